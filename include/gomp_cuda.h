@@ -1,0 +1,163 @@
+/*
+ * gomp_cuda.h -- C ABI of libgomp_cuda, the B200-native batched OSQP-style ADMM solver for
+ * GOMP trajectory QPs.
+ *
+ * The reference has no FFI: its seam is the C++ class QPSolver (reference
+ * src/osqp-wrapper.h:12-60), a shim over osqp::OsqpSolver.  Every entry point below
+ * replaces one of that class's members for a whole batch of QPs that share a sparsity
+ * pattern; the header-only facade in osqp-solver_b200/include/gomp/osqp-wrapper.h binds
+ * them back to the reference's signatures.
+ *
+ *   gomp_batch_create        <- QPSolver::QPSolver(c, P)      osqp-wrapper.h:16-31
+ *   gomp_batch_setup         <- constructing a fresh QPSolver on the same pattern
+ *                               (reference src/gomp-solver.h:61-64, once per horizon)
+ *   gomp_batch_warm_start_x  <- QPSolver::setWarmStart        osqp-wrapper.h:45-49
+ *   gomp_batch_solve         <- QPSolver::solve               osqp-wrapper.h:51-54
+ *   gomp_batch_update        <- QPSolver::update              osqp-wrapper.h:33-43
+ *   gomp_batch_get           <- solver.primal_solution()      osqp-wrapper.h:53
+ *   gomp_settings_default    <- osqp::OsqpSettings defaults   osqp-wrapper.h:26-27
+ *
+ * Conventions: plain pointers and sizes, int return codes (0 = OK), no exceptions, no
+ * C++/torch types.  Every data pointer may be a HOST or a DEVICE pointer (detected with
+ * cudaPointerGetAttributes); the library copies what it needs during the call, so no
+ * caller buffer has to outlive a call (as with osqp-cpp, SURVEY.md 8b "Ownership").
+ * One handle is not thread-safe; distinct handles are.  All arithmetic is fp64.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef GOMP_CUDA_H
+#define GOMP_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* return codes */
+#define GOMP_OK 0
+#define GOMP_ERR_INVALID_ARGUMENT 1 /* bad sizes / l > u / pattern mismatch (update throws in the reference) */
+#define GOMP_ERR_CUDA 2             /* a CUDA runtime call failed; see gomp_last_error_string() */
+#define GOMP_ERR_NO_DEVICE 3        /* no usable CUDA device: there is no CPU fallback */
+#define GOMP_ERR_UNSUPPORTED 4      /* structure outside what the kernels handle (e.g. block too large) */
+#define GOMP_ERR_ALLOC 5
+
+/* per-problem exit codes: numerically equal to osqp-cpp's OsqpExitCode
+ * (reference src/utils.h:11 `using ExitCode = osqp::OsqpExitCode`) */
+#define GOMP_EXIT_OPTIMAL 0
+#define GOMP_EXIT_PRIMAL_INFEASIBLE 1
+#define GOMP_EXIT_DUAL_INFEASIBLE 2
+#define GOMP_EXIT_OPTIMAL_INACCURATE 3
+#define GOMP_EXIT_PRIMAL_INFEASIBLE_INACCURATE 4
+#define GOMP_EXIT_DUAL_INFEASIBLE_INACCURATE 5
+#define GOMP_EXIT_MAX_ITERATIONS 6
+#define GOMP_EXIT_INTERRUPTED 7
+#define GOMP_EXIT_TIME_LIMIT 8
+#define GOMP_EXIT_NON_CONVEX 9
+#define GOMP_EXIT_UNKNOWN 10
+
+/* linear-system back ends */
+#define GOMP_LINSYS_AUTO 0
+#define GOMP_LINSYS_BLOCKTRI_SMEM 1   /* block-tridiagonal reduced KKT, factor resident in shared memory */
+#define GOMP_LINSYS_BLOCKTRI_GLOBAL 2 /* same factorisation, factor in L2/HBM (long horizons) */
+#define GOMP_LINSYS_PCG 3             /* reduced-KKT preconditioned CG (long horizons) */
+
+typedef struct gomp_batch gomp_batch;
+
+/* OSQP settings (defaults = OSQP 0.6 defaults as exposed by osqp::OsqpSettings, except
+ * adaptive_rho_interval, which OSQP derives from wall-clock time when 0 and which is
+ * therefore pinned to 25 here) plus device-side knobs. */
+typedef struct gomp_settings {
+    double rho;                    /* 0.1 */
+    double sigma;                  /* 1e-6 */
+    double alpha;                  /* 1.6 */
+    int32_t scaling;               /* 10 */
+    int32_t adaptive_rho;          /* 1 */
+    int32_t adaptive_rho_interval; /* 25 (pinned; must be a multiple of check_termination, >0) */
+    double adaptive_rho_tolerance; /* 5 */
+    int32_t max_iter;              /* 4000 */
+    double eps_abs;                /* 1e-3 */
+    double eps_rel;                /* 1e-3 */
+    double eps_prim_inf;           /* 1e-4 */
+    double eps_dual_inf;           /* 1e-4 */
+    int32_t scaled_termination;    /* 0 */
+    int32_t check_termination;     /* 25 */
+    int32_t warm_start;            /* 1 */
+    int32_t verbose;               /* 0 (the reference sets true; output only) */
+    /* device side */
+    int32_t device;                /* CUDA device ordinal, -1 = current */
+    void *stream;                  /* cudaStream_t to launch on, NULL = a stream owned by the handle */
+    int32_t linsys;                /* GOMP_LINSYS_* */
+    int32_t block_size;            /* stage-block size of the variable ordering, 0 = detect */
+    const int64_t *var_order;      /* n entries: position p holds variable var_order[p]; NULL = detect */
+    int32_t threads_per_cta;       /* 0 = auto */
+    int32_t borrow_inputs;         /* 1: device-pointer inputs are used in place (caller keeps them alive until the next setup/update) */
+} gomp_settings;
+
+typedef struct gomp_info {
+    int64_t batch, n, m, m_used, nnzA, nnzP;
+    int32_t block_size, num_blocks, offdiag_width;
+    int32_t linsys, threads_per_cta, ctas_per_sm, num_sms, grid;
+    int64_t smem_bytes;            /* dynamic shared memory per CTA */
+    int64_t workspace_bytes;       /* device memory owned by the handle */
+    int64_t kernel_launches;       /* launches issued by this handle so far */
+    double last_solve_ms;          /* device time of the last gomp_batch_solve (CUDA events on its stream) */
+    double last_h2d_ms;            /* device time of input copies in the last setup/update */
+    int64_t flops_per_iter;        /* algorithmic fp64 flops of one ADMM iteration of one QP */
+    int64_t smem_bytes_per_iter;   /* algorithmic shared-memory bytes moved by one ADMM iteration */
+    int64_t flops_per_factor, smem_bytes_per_factor;
+    int64_t flops_per_scaling, smem_bytes_per_scaling;
+    int64_t flops_per_check, smem_bytes_per_check;
+} gomp_info;
+
+int gomp_settings_default(gomp_settings *s);
+
+/* Build a batch of `batch` QPs  min 1/2 x'Px + q'x  s.t.  l <= Ax <= u  that share P and the
+ * CSC pattern of A.  P: CSC, full symmetric or upper triangular (only the upper triangle is
+ * used, as osqp-cpp does).  A_val: [batch, nnzA] (CSC order), l,u: [batch, m], q: [batch, n]
+ * or NULL (the reference always passes q = 0, osqp-wrapper.h:22).  Index arrays are host
+ * pointers.  Does the symbolic analysis (ordering, block structure, assembly maps) on the
+ * host and loads the data; numeric setup (Ruiz scaling, rho_vec, factorisation) runs on the
+ * device inside the first solve. */
+int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t batch, int64_t n,
+                      int64_t m, const int64_t *P_colptr, const int64_t *P_rowidx,
+                      const double *P_val, const int64_t *A_colptr, const int64_t *A_rowidx,
+                      const double *A_val, const double *l, const double *u, const double *q);
+
+/* Re-initialise every QP of the batch with new data as if freshly constructed (iterates and
+ * rho reset: a cold start) while re-using the symbolic analysis. */
+int gomp_batch_setup(gomp_batch *h, const double *A_val, const double *l, const double *u,
+                     const double *q);
+
+/* x0: [batch, n]; x <- Dinv x0, z <- A x, y untouched (OSQP osqp_warm_start_x). */
+int gomp_batch_warm_start_x(gomp_batch *h, const double *x0);
+
+/* Run ADMM on every QP until its own termination test fires.  Iterates, rho and the
+ * factorisation state persist on the device across calls. */
+int gomp_batch_solve(gomp_batch *h);
+
+/* New A values (same pattern), bounds and/or q; each pointer may be NULL = unchanged.
+ * Iterates and rho are kept (warm start), scaling is recomputed, the KKT refactored. */
+int gomp_batch_update(gomp_batch *h, const double *A_val, const double *l, const double *u,
+                      const double *q);
+
+/* Results of the last solve.  Any pointer may be NULL.  x: [batch, n], y: [batch, m],
+ * exit_code/iters/rho_updates: [batch] int32.  x, y are NaN for infeasible problems. */
+int gomp_batch_get(gomp_batch *h, double *x, double *y, int32_t *exit_code, int32_t *iters,
+                   int32_t *rho_updates);
+
+/* Extra per-problem diagnostics: pri_res, dua_res, rho, obj_val: [batch] or NULL. */
+int gomp_batch_get_info(gomp_batch *h, double *pri_res, double *dua_res, double *rho,
+                        double *obj_val);
+
+int gomp_batch_info(gomp_batch *h, gomp_info *info);
+int gomp_batch_sync(gomp_batch *h);
+int gomp_batch_destroy(gomp_batch *h);
+
+const char *gomp_last_error_string(void);
+int gomp_device_count(void);
+const char *gomp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOMP_CUDA_H */

@@ -1,0 +1,137 @@
+"""ctypes view of libgomp_host (include/gomp_problem.h): synthetic GOMP trajectory QPs.
+
+The generator runs the C++ facade's ConstraintBuilder<N> (the drop-in for reference
+src/constraints/constraint-builder.h) for every problem of a batch; see DESIGN.md for the
+concrete instance definition.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class ProblemConfig(C.Structure):
+    _fields_ = [
+        ("n_dim", C.c_int32), ("waypoints", C.c_int32), ("time_step", C.c_double),
+        ("pos_limit", C.c_double), ("vel_limit", C.c_double), ("acc_limit", C.c_double),
+        ("n_balls", C.c_int32), ("n_obstacles", C.c_int32), ("z_floor", C.c_double), ("seed", C.c_uint64),
+    ]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libgomp_host.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(path)
+        for name in ("gomp_problem_default_config", "gomp_problem_dims", "gomp_problem_pattern",
+                     "gomp_problem_generate", "gomp_problem_relinearize", "gomp_problem_check", "gomp_problem_fk"):
+            getattr(L, name).restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def default_config(**kw):
+    cfg = ProblemConfig()
+    lib().gomp_problem_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise KeyError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Pattern:
+    """Shared structure of one problem family: dims, CSC patterns of A and P, stage order."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        n, m, nnzA, nnzP = (C.c_int64() for _ in range(4))
+        rc = lib().gomp_problem_dims(C.byref(cfg), C.byref(n), C.byref(m), C.byref(nnzA), C.byref(nnzP))
+        if rc:
+            raise ValueError("invalid gomp_problem_config")
+        self.n, self.m, self.nnzA, self.nnzP = n.value, m.value, nnzA.value, nnzP.value
+        self.A_colptr = np.zeros(self.n + 1, dtype=np.int64)
+        self.A_rowidx = np.zeros(self.nnzA, dtype=np.int64)
+        self.P_colptr = np.zeros(self.n + 1, dtype=np.int64)
+        self.P_rowidx = np.zeros(self.nnzP, dtype=np.int64)
+        self.P_val = np.zeros(self.nnzP, dtype=np.float64)
+        self.var_order = np.zeros(self.n, dtype=np.int64)
+        rc = lib().gomp_problem_pattern(C.byref(cfg), _p(self.A_colptr), _p(self.A_rowidx), _p(self.P_colptr),
+                                        _p(self.P_rowidx), _p(self.P_val), _p(self.var_order))
+        if rc:
+            raise ValueError("gomp_problem_pattern failed")
+        self.block_size = 2 * cfg.n_dim
+
+    def P_scipy(self):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self.P_val, self.P_rowidx, self.P_colptr), shape=(self.n, self.n))
+
+    def A_scipy(self, A_val):
+        import scipy.sparse as sp
+        return sp.csc_matrix((A_val, self.A_rowidx, self.A_colptr), shape=(self.m, self.n))
+
+
+def generate(pattern, first_id, count, nthreads=0, out=None):
+    """A_val [count, nnzA], l, u [count, m], x0 [count, n], start_goal [count, 2N].
+
+    `out` may hold preallocated arrays (e.g. views of pinned torch tensors) under the same keys."""
+    cfg = pattern.cfg
+    out = dict(out or {})
+    shapes = dict(A_val=(count, pattern.nnzA), l=(count, pattern.m), u=(count, pattern.m), x0=(count, pattern.n),
+                  start_goal=(count, 2 * cfg.n_dim))
+    for k, shp in shapes.items():
+        if k not in out:
+            out[k] = np.empty(shp, dtype=np.float64)
+        assert out[k].shape == shp and out[k].dtype == np.float64 and out[k].flags.c_contiguous
+    rc = lib().gomp_problem_generate(C.byref(cfg), C.c_int64(first_id), C.c_int64(count), _p(out["A_val"]), _p(out["l"]),
+                                     _p(out["u"]), _p(out["x0"]), _p(out["start_goal"]), C.c_int32(nthreads))
+    if rc:
+        raise ValueError("gomp_problem_generate failed")
+    return out
+
+
+def relinearize(pattern, first_id, x, nthreads=0, out=None):
+    """One SQP round (reference src/gomp-solver.h:83-87): new A_val, l, u around trajectories x [count, n]."""
+    cfg = pattern.cfg
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    count = x.shape[0]
+    out = dict(out or {})
+    shapes = dict(A_val=(count, pattern.nnzA), l=(count, pattern.m), u=(count, pattern.m))
+    for k, shp in shapes.items():
+        if k not in out:
+            out[k] = np.empty(shp, dtype=np.float64)
+    rc = lib().gomp_problem_relinearize(C.byref(cfg), C.c_int64(first_id), C.c_int64(count), _p(x), _p(out["A_val"]),
+                                        _p(out["l"]), _p(out["u"]), C.c_int32(nthreads))
+    if rc:
+        raise ValueError("gomp_problem_relinearize failed")
+    return out
+
+
+def check(pattern, first_id, x, nthreads=0):
+    """isSolutionOK (reference src/gomp-solver.h:141-199) per trajectory."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    ok = np.zeros(x.shape[0], dtype=np.int32)
+    rc = lib().gomp_problem_check(C.byref(pattern.cfg), C.c_int64(first_id), C.c_int64(x.shape[0]), _p(x), _p(ok),
+                                  C.c_int32(nthreads))
+    if rc:
+        raise ValueError("gomp_problem_check failed")
+    return ok.astype(bool)
+
+
+def fk(cfg, q, ball=0, want_jac=False):
+    q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, cfg.n_dim)
+    xyz = np.zeros((q.shape[0], 3))
+    jac = np.zeros((q.shape[0], 3, cfg.n_dim)) if want_jac else None
+    rc = lib().gomp_problem_fk(C.byref(cfg), C.c_int32(ball), C.c_int64(q.shape[0]), _p(q), _p(xyz), _p(jac))
+    if rc:
+        raise ValueError("gomp_problem_fk failed")
+    return (xyz, jac) if want_jac else xyz
