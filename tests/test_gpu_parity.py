@@ -1,0 +1,297 @@
+"""CUDA hot path (through the C ABI, include/gomp_cuda.h) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): same solver status, iteration counts within +-10% (here: equal),
+primal/dual solutions within 1e-6 relative -- demonstrated where both solvers converge to the
+optimum (tight eps) and, at the default eps = 1e-3, as agreement of the iterates themselves because
+the two implementations perform the same ADMM steps (different linear-system factorisations).
+The oracle is a restatement of OSQP, not genuine OSQP: parity unpinned (oracle/osqp_ref.h).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from common import oracle, package
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-6  # north_star: primal/dual within 1e-6 relative
+
+
+def make_solver(pkg, pat, d, settings=None, **kw):
+    return pkg.solver.BatchQPSolver(pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx,
+                                    d["A_val"], d["l"], d["u"], settings=settings, var_order=pat.var_order,
+                                    block_size=pat.block_size, **kw)
+
+
+def compare(got, ref, want_y=True):
+    assert (got["exit_code"] == ref["exit_code"]).all(), (got["exit_code"], ref["exit_code"])
+    assert (got["iters"] == ref["iters"]).all(), (got["iters"], ref["iters"])
+    assert (got["rho_updates"] == ref["rho_updates"]).all()
+    ok = ref["exit_code"] == 0
+    bad = ~ok & np.isin(ref["exit_code"], [1, 2, 4, 5])  # infeasible: NaN solution on both sides
+    assert np.isnan(got["x"][bad]).all() and np.isnan(ref["x"][bad]).all()
+    if ok.any():
+        scale = np.abs(ref["x"][ok]).max(axis=1, keepdims=True)
+        assert (np.abs(got["x"][ok] - ref["x"][ok]) / scale).max() < REL_TOL
+        if want_y:
+            ys = np.maximum(np.abs(ref["y"][ok]).max(axis=1, keepdims=True), 1e-3)
+            assert (np.abs(got["y"][ok] - ref["y"][ok]) / ys).max() < REL_TOL
+
+
+@pytest.fixture(scope="module")
+def env():
+    pkg, O = package(), oracle()
+    cfg = pkg.problem.default_config()
+    pat = pkg.problem.Pattern(cfg)
+    return pkg, O, pat
+
+
+def oracle_batch(O, pat, d, settings=None):
+    return O.solve_batch(pat.n, pat.m, pat.P_scipy(), (pat.A_colptr, pat.A_rowidx), d["A_val"], d["l"], d["u"], d["x0"],
+                         settings=settings, want_y=True)
+
+
+def test_gomp_batch_default_settings(env):
+    """BASELINE configs[1] shape (7-DoF, H=50), 96 problems incl. multi-check and infeasible ones."""
+    pkg, O, pat = env
+    d = pkg.problem.generate(pat, 0, 96)
+    s = make_solver(pkg, pat, d)
+    s.set_warm_start(d["x0"])
+    got = s.solve(want_y=True)
+    ref = oracle_batch(O, pat, d)
+    compare(got, ref)
+    assert (ref["exit_code"] != 0).any() and (ref["iters"] > 25).any()  # the sample exercises those paths
+    info = s.info()
+    assert info["m_used"] == 1558 and info["block_size"] == 14 and info["num_blocks"] == 50
+    s.close()
+
+
+def test_gomp_tight_tolerance_solution_parity(env):
+    """eps = 1e-8: both converge to the optimum, x and y agree to 1e-6 relative."""
+    pkg, O, pat = env
+    d = pkg.problem.generate(pat, 100, 24)
+    st = pkg.solver.default_settings(eps_abs=1e-8, eps_rel=1e-8)
+    s = make_solver(pkg, pat, d, settings=st)
+    s.set_warm_start(d["x0"])
+    got = s.solve(want_y=True)
+    ref = oracle_batch(O, pat, d, settings=O.default_settings(eps_abs=1e-8, eps_rel=1e-8))
+    compare(got, ref)
+    s.close()
+
+
+def test_sqp_update_sequence(env):
+    """BASELINE configs[2]: solve -> withObstacles(x) -> update(A, l, u) -> solve, 5 rounds
+    (reference src/gomp-solver.h:70-88); iterates and rho persist on the device."""
+    pkg, O, pat = env
+    B = 12
+    d = pkg.problem.generate(pat, 200, B)
+    s = make_solver(pkg, pat, d)
+    s.set_warm_start(d["x0"])
+    Ps = pat.P_scipy()
+    refs = [O.Solver(Ps, pat.A_scipy(d["A_val"][b]), d["l"][b], d["u"][b]) for b in range(B)]
+    for b in range(B):
+        refs[b].warm_start_x(d["x0"][b])
+    for rnd in range(5):
+        got = s.solve(want_y=True)
+        for b in range(B):
+            refs[b].solve()
+        ref = dict(x=np.array([r.x for r in refs]), y=np.array([r.y for r in refs]),
+                   exit_code=np.array([r.exit_code for r in refs]), iters=np.array([r.iter for r in refs]),
+                   rho_updates=np.array([r.rho_updates for r in refs]))
+        compare(got, ref)
+        xs = np.where(np.isnan(ref["x"]), d["x0"], ref["x"])
+        upd = pkg.problem.relinearize(pat, 200, xs)
+        s.update(upd["A_val"], upd["l"], upd["u"])
+        for b in range(B):
+            refs[b].update(upd["A_val"][b], upd["l"][b], upd["u"][b])
+    s.close()
+
+
+def test_setup_resets_state(env):
+    """gomp_batch_setup == constructing a fresh QPSolver: same answer as the first cold solve."""
+    pkg, O, pat = env
+    d = pkg.problem.generate(pat, 300, 8)
+    s = make_solver(pkg, pat, d)
+    s.set_warm_start(d["x0"])
+    first = s.solve()
+    s.solve()  # moves iterates / rho
+    s.setup(d["A_val"], d["l"], d["u"])
+    s.set_warm_start(d["x0"])
+    again = s.solve()
+    np.testing.assert_array_equal(first["x"], again["x"])
+    np.testing.assert_array_equal(first["iters"], again["iters"])
+    s.close()
+
+
+def test_batch_equals_single(env):
+    """Determinism: a QP solved inside a batch gives bit-identical results to the same QP alone."""
+    pkg, O, pat = env
+    d = pkg.problem.generate(pat, 400, 40)
+    s = make_solver(pkg, pat, d)
+    s.set_warm_start(d["x0"])
+    full = s.solve(want_y=True)
+    s.close()
+    for b in (0, 17, 39):
+        one = {k: v[b:b + 1] for k, v in d.items()}
+        s1 = make_solver(pkg, pat, one)
+        s1.set_warm_start(one["x0"])
+        r = s1.solve(want_y=True)
+        np.testing.assert_array_equal(r["x"][0], full["x"][b])
+        np.testing.assert_array_equal(r["y"][0], full["y"][b])
+        assert r["iters"][0] == full["iters"][b]
+        s1.close()
+
+
+def test_device_resident_inputs(env):
+    """Device pointers (torch CUDA tensors), borrowed in place, give the same answer as host inputs."""
+    import torch
+    pkg, O, pat = env
+    d = pkg.problem.generate(pat, 500, 16)
+    s = make_solver(pkg, pat, d)
+    s.set_warm_start(d["x0"])
+    host = s.solve()
+    s.close()
+    dd = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    st = pkg.solver.default_settings(borrow_inputs=1)
+    s2 = make_solver(pkg, pat, dd, settings=st, batch=16)
+    s2.set_warm_start(dd["x0"])
+    s2.solve_async()
+    xdev = torch.empty((16, pat.n), dtype=torch.float64, device="cuda")
+    r = s2.get(x=xdev)
+    np.testing.assert_array_equal(host["x"], xdev.cpu().numpy())
+    np.testing.assert_array_equal(host["iters"], r["iters"])
+    s2.close()
+
+
+@pytest.mark.parametrize("kw", [dict(n_dim=6), dict(n_balls=2, n_obstacles=2), dict(waypoints=12), dict(n_dim=3, waypoints=20)])
+def test_other_shapes(kw):
+    """6-DoF (block 12, generic kernel), the heavy 2-ball/2-line variant, short horizons."""
+    pkg, O = package(), oracle()
+    cfg = pkg.problem.default_config(**kw)
+    pat = pkg.problem.Pattern(cfg)
+    d = pkg.problem.generate(pat, 0, 24)
+    s = make_solver(pkg, pat, d)
+    s.set_warm_start(d["x0"])
+    got = s.solve(want_y=True)
+    ref = oracle_batch(O, pat, d)
+    compare(got, ref)
+    s.close()
+
+
+def random_qp(rng, n, m, density=0.4):
+    M = rng.standard_normal((n, n))
+    P = sp.csc_matrix(np.triu(M @ M.T + 0.1 * np.eye(n)))
+    A = rng.standard_normal((m, n)) * (rng.random((m, n)) < density)
+    A[0, :] = rng.standard_normal(n)  # at least one dense row keeps every column coupled
+    return P, sp.csc_matrix(A)
+
+
+def test_general_qp_with_linear_term():
+    """Generic path: no ordering hint (RCM + detected block size), q != 0, batch of random QPs with
+    a shared pattern; includes loose, equality and inequality rows."""
+    pkg, O = package(), oracle()
+    rng = np.random.default_rng(7)
+    n, m, B = 12, 18, 10
+    P, A = random_qp(rng, n, m)
+    A.sort_indices()
+    nnz = A.nnz
+    Ax = np.stack([A.data * (1 + 0.1 * rng.standard_normal(nnz)) for _ in range(B)])
+    l = -rng.random((B, m)) - 0.1
+    u = rng.random((B, m)) + 0.1
+    l[:, 3] = u[:, 3] = 0.05      # equality row
+    l[:, 5], u[:, 5] = -1e30, 1e30  # loose row
+    u[:, 7] = 1e30                  # one-sided
+    q = rng.standard_normal((B, n))
+    st = pkg.solver.default_settings(eps_abs=1e-7, eps_rel=1e-7)
+    s = pkg.solver.BatchQPSolver(n, m, P.indptr, P.indices, P.data, A.indptr, A.indices, Ax, l, u, q=q, settings=st)
+    got = s.solve(want_y=True)
+    s.close()
+    ost = O.default_settings(eps_abs=1e-7, eps_rel=1e-7)
+    for b in range(B):
+        Ab = sp.csc_matrix((Ax[b], A.indices, A.indptr), shape=(m, n))
+        r = O.Solver(P, Ab, l[b], u[b], q=q[b], settings=ost)
+        r.solve()
+        assert got["exit_code"][b] == r.exit_code and got["iters"][b] == r.iter
+        assert np.abs(got["x"][b] - r.x).max() < REL_TOL * max(1.0, np.abs(r.x).max())
+        assert np.abs(got["y"][b] - r.y).max() < REL_TOL * max(1.0, np.abs(r.y).max())
+
+
+def test_infeasible_and_unbounded():
+    """Known-answer status tests: primal infeasible (x in [1,2] and x in [-5,0]), dual infeasible
+    (min -x s.t. x >= 0), empty row whose bounds exclude 0."""
+    pkg, O = package(), oracle()
+    S = pkg.solver
+    P = sp.csc_matrix(np.eye(2))
+    A = sp.csc_matrix(np.array([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0]]))
+    s = S.BatchQPSolver(2, 3, P.indptr, P.indices, P.data, A.indptr, A.indices, A.data[None, :],
+                        np.array([[1.0, -5.0, -1.0]]), np.array([[2.0, 0.0, 1.0]]))
+    r = s.solve()
+    ref = O.Solver(P, A, np.array([1.0, -5.0, -1.0]), np.array([2.0, 0.0, 1.0]))
+    ref.solve()
+    assert r["exit_code"][0] == ref.exit_code == 1 and r["iters"][0] == ref.iter
+    assert np.isnan(r["x"]).all()
+    s.close()
+
+    P0 = sp.csc_matrix((1, 1))
+    A1 = sp.csc_matrix(np.array([[1.0]]))
+    s = S.BatchQPSolver(1, 1, P0.indptr, P0.indices, P0.data, A1.indptr, A1.indices, A1.data[None, :],
+                        np.array([[0.0]]), np.array([[1e30]]), q=np.array([[-1.0]]))
+    r = s.solve()
+    ref = O.Solver(P0, A1, np.array([0.0]), np.array([1e30]), q=np.array([-1.0]))
+    ref.solve()
+    assert r["exit_code"][0] == ref.exit_code == 2 and r["iters"][0] == ref.iter
+    s.close()
+
+    A2 = sp.csc_matrix(np.array([[1.0, 0.0], [0.0, 0.0]]))  # second row empty, bounds [1, 2] exclude 0
+    s = S.BatchQPSolver(2, 2, P.indptr, P.indices, P.data, A2.indptr, A2.indices, A2.data[None, :],
+                        np.array([[-1.0, 1.0]]), np.array([[1.0, 2.0]]))
+    r = s.solve()
+    assert r["exit_code"][0] == 1
+    s.close()
+
+
+def test_update_rejects_bad_bounds(env):
+    """QPSolver::update throws std::invalid_argument on a failed SetBounds (reference
+    src/osqp-wrapper.h:40-42); the C ABI returns GOMP_ERR_INVALID_ARGUMENT."""
+    pkg, O, pat = env
+    d = pkg.problem.generate(pat, 0, 2)
+    s = make_solver(pkg, pat, d)
+    bad_l = d["u"] + 1.0
+    with pytest.raises(pkg.solver.GompError) as e:
+        s.update(None, bad_l, d["u"])
+    assert e.value.code == 1
+    s.close()
+
+
+def test_full_size_batch_properties(env):
+    """BASELINE configs[1] at full size (4096 QPs): size-independent properties instead of the
+    oracle -- every optimal solution satisfies its own stopping criterion when re-evaluated on the
+    host in fp64, iteration counts are multiples of check_termination, and a repeated solve of the
+    same batch is bit-identical."""
+    pkg, O, pat = env
+    B = 4096
+    d = pkg.problem.generate(pat, 0, B)
+    s = make_solver(pkg, pat, d)
+    s.set_warm_start(d["x0"])
+    r = s.solve(want_y=True)
+    assert (r["iters"] % 25 == 0).all() and (r["iters"] >= 25).all()
+    ok = r["exit_code"] == 0
+    assert ok.mean() > 0.85
+    P = pat.P_scipy()
+    idx = np.flatnonzero(ok)[:: max(1, ok.sum() // 200)]  # ~200 spread samples
+    for b in idx:
+        A = pat.A_scipy(d["A_val"][b])
+        x, y = r["x"][b], r["y"][b]
+        Ax = A @ x
+        zproj = np.clip(Ax, d["l"][b], d["u"][b])
+        pri = np.abs(Ax - zproj).max()
+        dua = np.abs(P @ x + A.T @ y).max()
+        # OSQP stops on ||Ax - z||, z the ADMM iterate; the projection distance is bounded by it
+        assert pri <= 1e-3 + 1e-3 * np.abs(Ax).max() + 1e-9
+        assert dua <= 1e-3 + 1e-3 * max(np.abs(P @ x).max(), np.abs(A.T @ y).max()) + 1e-9
+    s.setup(d["A_val"], d["l"], d["u"])
+    s.set_warm_start(d["x0"])
+    r2 = s.solve(want_y=True)
+    np.testing.assert_array_equal(r["x"], r2["x"])
+    np.testing.assert_array_equal(r["iters"], r2["iters"])
+    s.close()
