@@ -107,6 +107,9 @@ typedef struct gomp_info {
     int64_t flops_per_factor, smem_bytes_per_factor;
     int64_t flops_per_scaling, smem_bytes_per_scaling;
     int64_t flops_per_check, smem_bytes_per_check;
+    double phase_cycles[8];        /* with env GOMP_PROFILE_PHASES=1 at create: SM cycles summed over all QPs per phase
+                                      (load, scaling, factor, rhs gather, block solve, x/z/y update, residuals+termination, store) */
+    double assemble_cycles;        /* part of phase_cycles[2] spent assembling S (all threads) */
 } gomp_info;
 
 int gomp_settings_default(gomp_settings *s);
@@ -152,6 +155,10 @@ int gomp_batch_get_info(gomp_batch *h, double *pri_res, double *dua_res, double 
 int gomp_batch_info(gomp_batch *h, gomp_info *info);
 int gomp_batch_sync(gomp_batch *h);
 int gomp_batch_destroy(gomp_batch *h);
+
+/* Measured roofline denominators of the current device for this kernel class: FP64 FMA throughput
+ * (TFLOP/s) and aggregate shared-memory load bandwidth (GB/s).  Either pointer may be NULL. */
+int gomp_measure_peaks(double *fp64_tflops, double *smem_gbs);
 
 const char *gomp_last_error_string(void);
 int gomp_device_count(void);

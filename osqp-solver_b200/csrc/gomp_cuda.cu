@@ -26,6 +26,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -40,8 +41,8 @@ using namespace gomp_dev;
     extern template cudaError_t gomp_dev::prepare_variant<R, C, BSZ>(size_t, int *);                 \
     extern template cudaError_t gomp_dev::launch_variant<R, C, BSZ>(const DevSym &, const DevBatch &, const DevSettings &, int, size_t, cudaStream_t);
 GOMP_DECLARE_VARIANT(2, 1, 0)
+GOMP_DECLARE_VARIANT(4, 2, 14)
 GOMP_DECLARE_VARIANT(4, 2, 0)
-GOMP_DECLARE_VARIANT(7, 3, 14)
 GOMP_DECLARE_VARIANT(8, 4, 0)
 
 namespace {
@@ -102,12 +103,12 @@ struct KernelChoice {
 // block size is used when it matches, otherwise the generic (runtime block size) variant
 KernelChoice pick_kernel(int m_used, int n_pad, int bs) {
     KernelChoice k;
-    const int need_r = std::max(1, (m_used + kThreads - 1) / kThreads), need_c = (n_pad + kThreads - 1) / kThreads;
+    const int need_r = std::max(1, (m_used + kOwners - 1) / kOwners), need_c = (n_pad + kOwners - 1) / kOwners;
     struct Opt { int r, c, b; PrepareFn p; LaunchFn l; };
     const Opt opts[] = {
         {2, 1, 0, prepare_variant<2, 1, 0>, launch_variant<2, 1, 0>},
+        {4, 2, 14, prepare_variant<4, 2, 14>, launch_variant<4, 2, 14>},
         {4, 2, 0, prepare_variant<4, 2, 0>, launch_variant<4, 2, 0>},
-        {7, 3, 14, prepare_variant<7, 3, 14>, launch_variant<7, 3, 14>},
         {8, 4, 0, prepare_variant<8, 4, 0>, launch_variant<8, 4, 0>},
     };
     for (const Opt &o : opts)
@@ -116,6 +117,38 @@ KernelChoice pick_kernel(int m_used, int n_pad, int bs) {
             return k;
         }
     return k;
+}
+
+// ---- roofline denominators measured on the device this library runs on ------------------------------
+// MEASURED_PEAKS.json only carries HBM and bf16 tensor numbers; the kernel here is bounded by the FP64
+// pipe and by shared-memory bandwidth, so both are measured with two tiny kernels.
+__global__ void peak_fp64_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void peak_smem_kernel(double *out, int iters) {
+    extern __shared__ __align__(16) double buf[];
+    const int words = 4096; // 32 KB of doubles per CTA
+    for (int i = threadIdx.x; i < words; i += blockDim.x) buf[i] = i * 1e-6;
+    __syncthreads();
+    const double2 *v = reinterpret_cast<const double2 *>(buf);
+    double2 acc = make_double2(0.0, 0.0);
+    int idx = threadIdx.x;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { // conflict-free 16-byte loads, 8 in flight
+            const double2 t = v[(idx + k * 256) & (words / 2 - 1)];
+            acc.x += t.x;
+            acc.y += t.y;
+        }
+        idx = (idx + 37) & (words / 2 - 1);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc.x + acc.y;
 }
 
 } // namespace
@@ -135,18 +168,20 @@ struct gomp_batch {
     int64_t batch = 0, launches = 0;
     double last_solve_ms = 0, last_h2d_ms = 0;
     bool has_q = false, data_loaded = false;
+    int pending_flags = 1; // bit0: cold start, bit1: warm start x pending -- consumed by the next solve
+    const double *x0_src = nullptr;
     // pattern arrays on the device
     DevArray<int32_t> d_pos_var, d_used_rows, d_empty_rows;
-    DevArray<uint32_t> d_row_ent, d_col_start, d_Pu_ij, d_pf_ent, d_sd_ptr, d_so_ptr;
-    DevArray<uint8_t> d_row_len, d_col_len, d_pf_len, d_sd_kind;
-    DevArray<uint16_t> d_col_row, d_offT_slot, d_sd_pk, d_so_pk;
+    DevArray<uint32_t> d_row_csr, d_col_range, d_pf_csr, d_Pu_ij, d_sd_ptr, d_so_ptr;
+    DevArray<uint16_t> d_row_ptr, d_csc_row, d_pf_ptr, d_offT_slot, d_sd_pk, d_so_pk, d_tri_rc;
+    DevArray<uint8_t> d_sd_kind;
     DevArray<int8_t> d_off_col, d_offT_row;
     DevArray<double> d_Pu_val;
     DevArray<gomp::Contrib> d_sd_con, d_so_con;
     // per-batch storage
     DevArray<double> d_A, d_l, d_u, d_q, d_x0, d_xs, d_zs, d_ys, d_rho, d_E, d_D, d_qs, d_dy, d_dx, d_xo, d_yo, d_pri, d_dua, d_obj;
-    DevArray<uint16_t> d_tri_rc;
-    DevArray<int> d_flags, d_status, d_iters, d_rup, d_counter;
+    DevArray<unsigned long long> d_prof;
+    DevArray<int> d_status, d_iters, d_rup, d_counter;
     const double *A_src = nullptr, *l_src = nullptr, *u_src = nullptr, *q_src = nullptr; // borrowed device inputs
     long long A_pitch = 0;
     std::vector<int> h_status;
@@ -160,15 +195,14 @@ int upload_pattern(gomp_batch *h) {
     UP(d_pos_var, pos_var);
     UP(d_used_rows, used_rows);
     UP(d_empty_rows, empty_rows);
-    UP(d_row_ent, row_ent);
-    UP(d_row_len, row_len);
-    UP(d_col_start, col_start);
-    UP(d_col_len, col_len);
-    UP(d_col_row, col_row);
+    UP(d_row_csr, row_csr);
+    UP(d_row_ptr, row_ptr);
+    UP(d_csc_row, csc_row);
+    UP(d_col_range, col_range);
+    UP(d_pf_csr, pf_csr);
+    UP(d_pf_ptr, pf_ptr);
     UP(d_Pu_val, Pu_val);
     UP(d_Pu_ij, Pu_ij);
-    UP(d_pf_ent, pf_ent);
-    UP(d_pf_len, pf_len);
     UP(d_off_col, off_col);
     UP(d_offT_row, offT_row);
     UP(d_offT_slot, offT_slot);
@@ -190,37 +224,43 @@ int upload_pattern(gomp_batch *h) {
 
     DevSym &d = h->ds;
     d.n = (int)s.n; d.m = (int)s.m; d.nnzA = (int)s.nnzA; d.nnzPu = (int)s.nnzPu; d.m_used = s.m_used; d.bs = s.bs;
-    d.T = s.T; d.n_pad = s.n_pad; d.roww = s.roww; d.colw = s.colw; d.ow = s.ow; d.owT = s.owT; d.dpb = s.dpb;
-    d.pfw = s.pfw; d.n_empty = (int)s.empty_rows.size(); d.noff = std::max(0, s.T - 1) * s.bs * s.ow;
-    // uniform off-diagonal pattern?
-    d.uniform_off = 1;
-    for (int t = 1; t + 1 < s.T && d.uniform_off; ++t) {
-        for (int e = 0; e < s.bs * s.ow; ++e)
-            if (s.off_col[(size_t)t * s.bs * s.ow + e] != s.off_col[e]) d.uniform_off = 0;
-        for (int e = 0; e < s.bs * s.owT; ++e)
-            if (s.offT_row[(size_t)t * s.bs * s.owT + e] != s.offT_row[e] || s.offT_slot[(size_t)t * s.bs * s.owT + e] != s.offT_slot[e])
-                d.uniform_off = 0;
-    }
-    if (s.T < 2) d.uniform_off = 0;
+    d.T = s.T; d.n_pad = s.n_pad; d.ow = s.ow; d.owT = s.owT;
+    d.n_empty = (int)s.empty_rows.size(); d.noff = std::max(0, s.T - 1) * s.bs * s.ow; d.npf = (int)s.pf_csr.size();
     d.pos_var = h->d_pos_var.p; d.used_rows = h->d_used_rows.p; d.empty_rows = h->d_empty_rows.p;
-    d.row_ent = h->d_row_ent.p; d.row_len = h->d_row_len.p; d.col_start = h->d_col_start.p; d.col_len = h->d_col_len.p;
-    d.col_row = h->d_col_row.p; d.Pu_val = h->d_Pu_val.p; d.Pu_ij = h->d_Pu_ij.p; d.pf_ent = h->d_pf_ent.p;
-    d.pf_len = h->d_pf_len.p; d.off_col = h->d_off_col.p; d.offT_row = h->d_offT_row.p; d.offT_slot = h->d_offT_slot.p;
+    d.row_csr = h->d_row_csr.p; d.col_range = h->d_col_range.p; d.pf_csr = h->d_pf_csr.p; d.Pu_ij = h->d_Pu_ij.p;
+    d.row_ptr = h->d_row_ptr.p; d.csc_row = h->d_csc_row.p; d.pf_ptr = h->d_pf_ptr.p; d.offT_slot = h->d_offT_slot.p;
+    d.off_col = h->d_off_col.p; d.offT_row = h->d_offT_row.p; d.Pu_val = h->d_Pu_val.p;
     d.sd_ptr = h->d_sd_ptr.p; d.sd_con = h->d_sd_con.p; d.sd_pk = h->d_sd_pk.p; d.sd_kind = h->d_sd_kind.p;
     d.so_ptr = h->d_so_ptr.p; d.so_con = h->d_so_con.p; d.so_pk = h->d_so_pk.p; d.tri_rc = h->d_tri_rc.p;
-    // shared-memory carve-up
-    auto even = [](int v) { return (v + 1) & ~1; };
-    int o = 0;
-    d.oA = o; o += even(d.nnzA);
-    d.oP = o; o += even(std::max(1, d.nnzPu));
-    d.oW = o; o += even(std::max(1, d.m_used));
-    d.oRHS = o; o += even(d.n_pad);
-    d.oDinv = o; o += even(d.T * d.dpb);
-    d.oOff = o; o += even(std::max(1, d.noff));
-    d.oInv = o; o += 2 * d.bs * d.bs;
-    d.oRed = o; o += kRedK * (kThreads / 32);
-    d.oEnd = o;
-    h->smem_bytes = (size_t)(o + 2) * sizeof(double);
+    // shared-memory carve-up (byte offsets; every region 16-byte aligned)
+    size_t o = 0;
+    auto take = [&o](size_t bytes) {
+        size_t at = o;
+        o += (bytes + 15) & ~(size_t)15;
+        return (int)at;
+    };
+    const size_t bb = (size_t)d.bs * d.bs, noffT = (size_t)std::max(0, d.T - 1) * d.bs * d.owT;
+    d.oA = take(8 * (size_t)d.nnzA);
+    d.oP = take(8 * (size_t)std::max(1, d.nnzPu));
+    d.oW = take(8 * (size_t)std::max(1, d.m_used));
+    d.oRHS = take(8 * (size_t)d.n_pad);
+    d.oDinv = take(8 * (size_t)d.T * bb);
+    d.oOff = take(8 * (size_t)std::max(1, d.noff));
+    d.oV = take(8 * 64);
+    d.oScr = take(8 * std::max<size_t>(2 * bb, 256)); // per-warp scratch (generic path) / pivot row+column exchange of the factor groups
+    d.oRed = take(8 * (size_t)kRedK * (kThreads / 32));
+    d.oRowEnt = take(4 * (size_t)d.nnzA);
+    d.oColRange = take(4 * (size_t)d.n_pad);
+    d.oPfEnt = take(4 * (size_t)std::max(1, d.npf));
+    d.oPuIJ = take(4 * (size_t)std::max(1, d.nnzPu));
+    d.oRowPtr = take(2 * ((size_t)d.m_used + 1));
+    d.oCscRow = take(2 * (size_t)d.nnzA);
+    d.oPfPtr = take(2 * ((size_t)d.n_pad + 1));
+    d.oOffTslot = take(2 * std::max<size_t>(1, noffT));
+    d.oOffCol = take(std::max<size_t>(1, (size_t)d.noff));
+    d.oOffTrow = take(std::max<size_t>(1, noffT));
+    d.oBar = take(16);
+    h->smem_bytes = o;
     return GOMP_OK;
 }
 
@@ -266,12 +306,7 @@ int load_data(gomp_batch *h, const double *A_val, const double *l, const double 
         h->has_q = true;
     }
     CUDA_TRY(cudaEventRecord(h->evc1, h->stream));
-    if (cold) {
-        // flags <- cold start (bit0), warm start cleared
-        std::vector<int> f(B, 1);
-        CUDA_TRY(cudaMemcpyAsync(h->d_flags.p, f.data(), B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
-    }
+    if (cold) h->pending_flags = 1; // cold start; a pending warm start belongs to the previous problem
     h->data_loaded = true;
     return GOMP_OK;
 }
@@ -318,6 +353,51 @@ int gomp_device_count(void) {
     return n;
 }
 
+int gomp_measure_peaks(double *fp64_tflops, double *smem_gbs) {
+    if (gomp_device_count() <= 0) return fail(GOMP_ERR_NO_DEVICE, "no CUDA device visible");
+    cudaDeviceProp prop;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    const int threads = 256, grid = prop.multiProcessorCount * 8;
+    double *out = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&out, (size_t)grid * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float ms = 0;
+    if (fp64_tflops) {
+        const int iters = 1 << 15;
+        double best = 0;
+        for (int rep = 0; rep < 4; ++rep) {
+            CUDA_TRY(cudaEventRecord(e0));
+            peak_fp64_kernel<<<grid, threads>>>(out, iters);
+            CUDA_TRY(cudaEventRecord(e1));
+            CUDA_TRY(cudaEventSynchronize(e1));
+            CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::max(best, 2.0 * 8.0 * iters * (double)grid * threads / (ms * 1e-3) / 1e12);
+        }
+        *fp64_tflops = best;
+    }
+    if (smem_gbs) {
+        const int iters = 1 << 13;
+        double best = 0;
+        for (int rep = 0; rep < 4; ++rep) {
+            CUDA_TRY(cudaEventRecord(e0));
+            peak_smem_kernel<<<grid, threads, 32768>>>(out, iters);
+            CUDA_TRY(cudaEventRecord(e1));
+            CUDA_TRY(cudaEventSynchronize(e1));
+            CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::max(best, 16.0 * 8.0 * iters * (double)grid * threads / (ms * 1e-3) / 1e9);
+        }
+        *smem_gbs = best;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return GOMP_OK;
+}
+
 const char *gomp_version(void) { return "gomp_cuda 0.1 (sm_100a)"; }
 const char *gomp_last_error_string(void) { return g_error.c_str(); }
 
@@ -325,15 +405,15 @@ int gomp_batch_destroy(gomp_batch *h) {
     if (!h) return GOMP_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    h->d_pos_var.release(); h->d_used_rows.release(); h->d_empty_rows.release(); h->d_row_ent.release();
-    h->d_col_start.release(); h->d_Pu_ij.release(); h->d_pf_ent.release(); h->d_sd_ptr.release(); h->d_so_ptr.release();
-    h->d_row_len.release(); h->d_col_len.release(); h->d_pf_len.release(); h->d_sd_kind.release(); h->d_col_row.release();
-    h->d_offT_slot.release(); h->d_sd_pk.release(); h->d_so_pk.release(); h->d_off_col.release(); h->d_offT_row.release();
-    h->d_Pu_val.release(); h->d_sd_con.release(); h->d_so_con.release();
+    h->d_pos_var.release(); h->d_used_rows.release(); h->d_empty_rows.release(); h->d_row_csr.release(); h->d_col_range.release();
+    h->d_pf_csr.release(); h->d_Pu_ij.release(); h->d_sd_ptr.release(); h->d_so_ptr.release(); h->d_row_ptr.release();
+    h->d_csc_row.release(); h->d_pf_ptr.release(); h->d_offT_slot.release(); h->d_sd_pk.release(); h->d_so_pk.release();
+    h->d_sd_kind.release(); h->d_off_col.release(); h->d_offT_row.release(); h->d_Pu_val.release(); h->d_sd_con.release();
+    h->d_so_con.release();
     h->d_A.release(); h->d_l.release(); h->d_u.release(); h->d_q.release(); h->d_x0.release(); h->d_xs.release();
     h->d_zs.release(); h->d_ys.release(); h->d_rho.release(); h->d_E.release(); h->d_D.release(); h->d_qs.release(); h->d_dx.release(); h->d_tri_rc.release(); h->d_dy.release(); h->d_xo.release();
-    h->d_yo.release(); h->d_pri.release(); h->d_dua.release(); h->d_obj.release(); h->d_flags.release();
-    h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release();
+    h->d_yo.release(); h->d_pri.release(); h->d_dua.release(); h->d_obj.release();
+    h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evc0) cudaEventDestroy(h->evc0);
@@ -395,7 +475,7 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
 
     h->kernel = pick_kernel(h->sym.m_used, h->sym.n_pad, h->sym.bs);
     if (!h->kernel.launch)
-        return bail(fail(GOMP_ERR_UNSUPPORTED, "problem too large for the register-resident kernel (m_used <= 2048, n <= 1024)"));
+        return bail(fail(GOMP_ERR_UNSUPPORTED, "problem too large for the register-resident kernel (non-empty rows <= 3584, variables <= 1792)"));
     if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
         return bail(fail(GOMP_ERR_UNSUPPORTED, "QP does not fit in shared memory (" + std::to_string(h->smem_bytes) + " bytes needed)"));
     int occ = 0;
@@ -428,11 +508,14 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     ALLOC(d_pri, B);
     ALLOC(d_dua, B);
     ALLOC(d_obj, B);
-    ALLOC(d_flags, B);
     ALLOC(d_status, B);
     ALLOC(d_iters, B);
     ALLOC(d_rup, B);
     ALLOC(d_counter, 1);
+    if (std::getenv("GOMP_PROFILE_PHASES")) {
+        ALLOC(d_prof, 16);
+        cudaMemsetAsync(h->d_prof.p, 0, 16 * sizeof(unsigned long long), h->stream);
+    }
 #undef ALLOC
     cudaMemsetAsync(h->d_rup.p, 0, B * sizeof(int), h->stream);
     cudaMemsetAsync(h->d_iters.p, 0, B * sizeof(int), h->stream);
@@ -467,16 +550,14 @@ int gomp_batch_warm_start_x(gomp_batch *h, const double *x0) {
     if (!h || !x0) return fail(GOMP_ERR_INVALID_ARGUMENT, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t B = (size_t)h->batch;
-    CUDA_TRY(cudaMemcpyAsync(h->d_x0.p, x0, B * (size_t)h->sym.n * sizeof(double),
-                             is_device_pointer(x0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
-    // flags |= 2  (tiny kernel-free path: read-modify-write on the host mirror is not possible without a sync,
-    // so the flag array is rewritten from the known state: cold bit is kept by OR-ing on the device side)
-    std::vector<int> f(B);
-    CUDA_TRY(cudaMemcpyAsync(f.data(), h->d_flags.p, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    for (auto &v : f) v |= 2;
-    CUDA_TRY(cudaMemcpyAsync(h->d_flags.p, f.data(), B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (is_device_pointer(x0) && h->st.borrow_inputs) {
+        h->x0_src = x0;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(h->d_x0.p, x0, B * (size_t)h->sym.n * sizeof(double),
+                                 is_device_pointer(x0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        h->x0_src = h->d_x0.p;
+    }
+    h->pending_flags |= 2;
     return GOMP_OK;
 }
 
@@ -487,18 +568,19 @@ int gomp_batch_solve(gomp_batch *h) {
     const gomp::Symbolic &s = h->sym;
     DevBatch &b = h->db;
     b.batch = (int)h->batch;
-    b.A_val = h->A_src; b.l = h->l_src; b.u = h->u_src; b.q = h->has_q ? h->q_src : nullptr; b.x0 = h->d_x0.p;
+    b.A_val = h->A_src; b.l = h->l_src; b.u = h->u_src; b.q = h->has_q ? h->q_src : nullptr; b.x0 = h->x0_src;
     b.A_pitch = s.nnzA;
     b.bulk_ok = (s.nnzA % 2 == 0) && (((uintptr_t)h->A_src) % 16 == 0) && s.nnzA > 0 && (size_t)s.nnzA * 8 < (1u << 20);
-    b.x_state = h->d_xs.p; b.z_state = h->d_zs.p; b.y_state = h->d_ys.p; b.rho_state = h->d_rho.p; b.flags = h->d_flags.p;
+    b.x_state = h->d_xs.p; b.z_state = h->d_zs.p; b.y_state = h->d_ys.p; b.rho_state = h->d_rho.p; b.flag_bits = h->pending_flags;
     b.Eg = h->d_E.p; b.Dg = h->d_D.p; b.qs = h->d_qs.p; b.dyg = h->d_dy.p; b.dxg = h->d_dx.p; b.x_out = h->d_xo.p; b.y_out = h->d_yo.p;
     b.status = h->d_status.p; b.iters = h->d_iters.p; b.rho_updates = h->d_rup.p;
-    b.pri_res = h->d_pri.p; b.dua_res = h->d_dua.p; b.obj_val = h->d_obj.p; b.work_counter = h->d_counter.p;
+    b.pri_res = h->d_pri.p; b.dua_res = h->d_dua.p; b.obj_val = h->d_obj.p; b.work_counter = h->d_counter.p; b.prof = h->d_prof.p;
     CUDA_TRY(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     CUDA_TRY(h->kernel.launch(h->ds, h->db, h->dst, h->grid, h->smem_bytes, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     h->launches++;
+    h->pending_flags = 0;
     return GOMP_OK;
 }
 
@@ -584,6 +666,13 @@ int gomp_batch_info(gomp_batch *h, gomp_info *info) {
     else cudaGetLastError();
     if (h->data_loaded && cudaEventQuery(h->evc1) == cudaSuccess && cudaEventElapsedTime(&ms, h->evc0, h->evc1) == cudaSuccess) h->last_h2d_ms = ms;
     else cudaGetLastError();
+    if (h->d_prof.p) {
+        unsigned long long pc[16];
+        if (cudaMemcpy(pc, h->d_prof.p, sizeof pc, cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (int k = 0; k < 8; ++k) info->phase_cycles[k] = (double)pc[k];
+            info->phase_cycles[2] += (double)pc[8]; // assembly is reported inside 'factor'
+            info->assemble_cycles = (double)pc[8];
+    }
     info->last_solve_ms = h->last_solve_ms;
     info->last_h2d_ms = h->last_h2d_ms;
     // algorithmic work of one QP (DESIGN.md "work model"); 1 FMA = 2 flops, shared-memory bytes = operands read + written

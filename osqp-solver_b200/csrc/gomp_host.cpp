@@ -22,6 +22,8 @@ constexpr double kForearmRadius = 0.15;
 constexpr double kLineDrop = 0.15;      // line sits this far below the higher end point
 constexpr double kMinEndpointZ = 0.05;  // start/goal gripper height is resampled above this
 constexpr double kSampleFraction = 0.6; // start/goal ~ U(+-0.6 * pos_limit)
+constexpr double kMinChordXY = 0.3;     // goal is resampled until the horizontal start->goal distance exceeds this,
+                                        // so that the obstacle line never passes within a ball radius of an end point
 
 template <int N>
 struct Scene {
@@ -70,7 +72,11 @@ Instance<N> drawInstance(const gomp_problem_config &cfg, const gomp::ArmGeometry
         }
     };
     draw(in.start, ps);
-    draw(in.goal, pg);
+    for (int tries = 0; tries < 1000; ++tries) {
+        draw(in.goal, pg);
+        const double cx = pg[0] - ps[0], cy = pg[1] - ps[1];
+        if (std::sqrt(cx * cx + cy * cy) >= kMinChordXY) break;
+    }
     // obstacle k: horizontal line perpendicular to the start->goal chord (XY), crossing it at
     // fraction (k+1)/(O+1), kLineDrop below the higher end point; passed from above.
     double dx = pg[0] - ps[0], dy = pg[1] - ps[1];

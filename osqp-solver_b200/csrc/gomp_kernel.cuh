@@ -1,14 +1,26 @@
 // gomp_kernel.cuh -- the persistent ADMM kernel of libgomp_cuda (sm_100a, fp64) and its launchers.
 //
-// One CTA pulls QPs from a device work queue and runs the whole OSQP algorithm for each of
-// them on chip (see gomp_cuda.cu for the overview).  Every kernel variant (rows per thread,
-// columns per thread, compile-time block size) is instantiated in its own translation unit
-// (gomp_kernel_inst.cu with -DGOMP_VARIANT=...), so variants compile in parallel.
+// One 512-thread CTA per SM pulls QPs from a device work queue and runs the whole OSQP algorithm
+// for each of them on chip.  Roles inside the CTA:
+//   * warps 0 and 1 are SOLVER warps.  They own the block-tridiagonal linear algebra: the two-way
+//     ("twisted") block factorisation of S = P + sigma I + A' diag(rho) A -- warp 0 eliminates
+//     stages 0..h-1 downwards, warp 1 stages T-1..h+1 upwards, they meet at the middle stage h --
+//     with explicit inverses of the pivot blocks (register-resident Gauss-Jordan, one matrix
+//     column per lane), and the forward / backward block substitutions of every ADMM iteration
+//     (one 2N x 2N GEMV per stage, operands broadcast through shared memory).
+//   * warps 2..15 are OWNER warps (448 threads).  Each thread owns a fixed set of constraint rows
+//     and variables; the ADMM iterates nobody else touches (z, y, l, u per row; x per variable)
+//     live in its REGISTERS for the whole solve.  Owners do the fused SpMV + projection + dual
+//     update, the A' gather, Ruiz equilibration, residuals and norms.
+// Shared memory holds what is exchanged: the QP's A values (staged with one TMA bulk copy,
+// cp.async.bulk + mbarrier), the scaled objective P, w = rho z - y, the right-hand side / x~, the
+// factor (full rows of every inverted pivot block + ELL off-diagonal blocks) and -- loaded once per
+// kernel, shared by every QP the CTA processes -- the sparsity-pattern index arrays.
 //
 // Algorithm per QP, following OSQP 0.6 as restated in oracle/osqp_ref.c:
-//   load -> Ruiz equilibration (10 passes) -> rho classification -> [warm start] ->
-//   { factor S = P + sigma I + A' diag(rho) A ; ADMM iterations ; every check_termination
-//     iterations residuals/termination/infeasibility ; adaptive rho -> refactor } -> store.
+//   load -> Ruiz equilibration -> rho classification -> [warm start] ->
+//   { factor ; ADMM iterations ; every check_termination iterations residuals / termination /
+//     infeasibility ; adaptive rho -> refactor } -> store.
 // Reference call sites replaced: src/osqp-wrapper.h:28 (Init), :46 (SetPrimalWarmStart),
 // :52 (Solve), :36,:40 (UpdateConstraintMatrix, SetBounds).
 #ifndef GOMP_KERNEL_CUH
@@ -26,24 +38,21 @@ namespace gomp_dev {
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqOverIneq = 1e3, kRhoTol = 1e-4;
 constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4, kInfty = 1e30, kDivTol = 1.0 / 1e30;
 
-constexpr int kThreads = 256;
-constexpr int kRedK = 14; // widest multi-value block reduction
+constexpr int kThreads = 512;              // 16 warps
+constexpr int kSolverThreads = 64;         // warps 0, 1
+constexpr int kOwners = kThreads - kSolverThreads; // 448 row / variable owners
+constexpr int kRedK = 14;                  // widest multi-value block reduction
 
 // ---- device-side views ------------------------------------------------------------------------
 struct DevSym {
-    int n, m, nnzA, nnzPu, m_used, bs, T, n_pad, roww, colw, ow, owT, dpb, pfw, n_empty, noff;
-    int uniform_off; // every off-diagonal block has the same pattern -> indices cached in registers
+    int n, m, nnzA, nnzPu, m_used, bs, T, n_pad, ow, owT, n_empty, noff, npf;
     const int32_t *pos_var, *used_rows, *empty_rows;
-    const uint32_t *row_ent;
-    const uint8_t *row_len;
-    const uint32_t *col_start;
-    const uint8_t *col_len;
-    const uint16_t *col_row;
-    const double *Pu_val;
-    const uint32_t *Pu_ij, *pf_ent;
-    const uint8_t *pf_len;
+    // pattern arrays (global copies; staged into shared memory once per kernel)
+    const uint32_t *row_csr, *col_range, *pf_csr, *Pu_ij;
+    const uint16_t *row_ptr, *csc_row, *pf_ptr, *offT_slot;
     const int8_t *off_col, *offT_row;
-    const uint16_t *offT_slot;
+    const double *Pu_val;
+    // assembly lists of S (global)
     const uint32_t *sd_ptr;
     const gomp::Contrib *sd_con;
     const uint16_t *sd_pk;
@@ -52,8 +61,9 @@ struct DevSym {
     const gomp::Contrib *so_con;
     const uint16_t *so_pk;
     const uint16_t *tri_rc; // packed lower index -> (row << 8 | col)
-    // shared-memory carve-up (in doubles)
-    int oA, oP, oW, oRHS, oDinv, oOff, oInv, oRed, oEnd;
+    // shared-memory carve-up (byte offsets)
+    int oA, oP, oW, oRHS, oDinv, oOff, oV, oScr, oRed, oRowEnt, oColRange, oPfEnt, oPuIJ, oRowPtr, oCscRow, oPfPtr, oOffTslot,
+        oOffCol, oOffTrow, oBar;
 };
 
 struct DevBatch {
@@ -62,12 +72,13 @@ struct DevBatch {
     const double *A_val, *l, *u, *q, *x0;
     long long A_pitch;
     double *x_state, *z_state, *y_state, *rho_state;
-    int *flags; // bit0: cold start, bit1: primal warm start pending
+    int flag_bits; // bit0: cold start, bit1: primal warm start pending (whole batch)
     double *Eg, *Dg, *qs, *dyg, *dxg;
     double *x_out, *y_out;
     int *status, *iters, *rho_updates;
     double *pri_res, *dua_res, *obj_val;
     int *work_counter;
+    unsigned long long *prof; // optional: per-phase cycle counters (thread 0 of every CTA adds), NULL = off
 };
 
 struct DevSettings {
@@ -102,18 +113,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// ---- block reductions (results broadcast to every thread; deterministic order) --------------------
-template <int K, int NT>
-__device__ __forceinline__ void block_max(double (&v)[K], double *sRed, int tid) {
-    constexpr int NW = NT / 32;
+// ---- reductions over the owner warps (named barrier 3; results broadcast to every owner; fixed order) ----
+__device__ __forceinline__ void owners_sync() { named_bar_sync(3, kOwners); }
+template <int K>
+__device__ __forceinline__ void owners_max(double (&v)[K], double *sRed, int oid) {
+    constexpr int NW = kOwners / 32;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double a = v[k];
 #pragma unroll
         for (int o = 16; o; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
-        if ((tid & 31) == 0) sRed[k * NW + (tid >> 5)] = a;
+        if ((oid & 31) == 0) sRed[k * NW + (oid >> 5)] = a;
     }
-    __syncthreads();
+    owners_sync();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double a = sRed[k * NW];
@@ -121,19 +133,18 @@ __device__ __forceinline__ void block_max(double (&v)[K], double *sRed, int tid)
         for (int j = 1; j < NW; ++j) a = fmax(a, sRed[k * NW + j]);
         v[k] = a;
     }
-    __syncthreads();
+    owners_sync();
 }
-template <int NT>
-__device__ __forceinline__ double block_sum(double a, double *sRed, int tid) {
-    constexpr int NW = NT / 32;
+__device__ __forceinline__ double owners_sum(double a, double *sRed, int oid) {
+    constexpr int NW = kOwners / 32;
 #pragma unroll
     for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if ((tid & 31) == 0) sRed[tid >> 5] = a;
-    __syncthreads();
+    if ((oid & 31) == 0) sRed[oid >> 5] = a;
+    owners_sync();
     double r = sRed[0];
 #pragma unroll
     for (int j = 1; j < NW; ++j) r += sRed[j];
-    __syncthreads();
+    owners_sync();
     return r;
 }
 
@@ -142,223 +153,590 @@ __device__ __forceinline__ double limit_scaling(double v) {
     return v > kMaxScaling ? kMaxScaling : v;
 }
 
-// ---- warp-level pieces of the block-tridiagonal factor / solve ---------------------------------------
-// u = Dinv_t * v, one entry of v and u per lane (lanes >= bs carry zeros).
-template <int BS>
-__device__ __forceinline__ double gemv_dinv(const double *__restrict__ Dt, double v, int lane, int bs) {
-    const int rl = lane < bs ? lane : bs - 1;
-    const int rbase = rl * (rl + 1) / 2;
-    double a0 = 0.0, a1 = 0.0;
-    if (BS > 0) {
-#pragma unroll
-        for (int c = 0; c < BS; ++c) {
-            const double vc = __shfl_sync(0xffffffffu, v, c);
-            const int idx = rl >= c ? rbase + c : c * (c + 1) / 2 + rl;
-            const double m = Dt[idx];
-            if (c & 1) a1 = fma(m, vc, a1);
-            else a0 = fma(m, vc, a0);
-        }
-    } else {
-        for (int c = 0; c < bs; ++c) {
-            const double vc = __shfl_sync(0xffffffffu, v, c);
-            const int idx = rl >= c ? rbase + c : c * (c + 1) / 2 + rl;
-            a0 = fma(Dt[idx], vc, a0);
-        }
-    }
-    const double r = a0 + a1;
-    return lane < bs ? r : 0.0;
-}
-
-struct OffIdx { // per-lane pattern of one off-diagonal block (<= 4 entries per row / column cached)
-    int col[4];
-    int trow[4];
-    int tslot[4];
+// Everything the solver warps need, all in shared memory.  Only the base pointer lives in a register;
+// the region offsets come straight from the kernel-parameter constant bank.
+struct SolverCtx {
+    uint32_t sm; // shared-window address of the dynamic shared memory base (keeps every access an LDS/STS)
+    int oDinv, oOff, oRHS, oV, oScr, oOffCol, oOffTrow, oOffTslot;
+    int bs, T, ow, owT;
+    template <typename U>
+    __device__ __forceinline__ U *at(int off) const { return reinterpret_cast<U *>(__cvta_shared_to_generic((size_t)(sm + (uint32_t)off))); }
+    __device__ __forceinline__ double *dinv() const { return at<double>(oDinv); }  // [T][bs][bs] inverted pivot blocks (full rows)
+    __device__ __forceinline__ double *off() const { return at<double>(oOff); }    // [(T-1)][bs][ow] ELL off-diagonal values
+    __device__ __forceinline__ double *rhs() const { return at<double>(oRHS); }    // [n_pad]
+    __device__ __forceinline__ double *vbuf() const { return at<double>(oV); }     // [32] per-warp broadcast buffer
+    __device__ __forceinline__ const int8_t *offCol() const { return at<const int8_t>(oOffCol); }
+    __device__ __forceinline__ const int8_t *offTrow() const { return at<const int8_t>(oOffTrow); }
+    __device__ __forceinline__ const uint16_t *offTslot() const { return at<const uint16_t>(oOffTslot); }
 };
-__device__ __forceinline__ void load_off_idx(const DevSym &S, int t, int lane, int bs, OffIdx &ix) {
+
+// u = M_row . v   (row of the lane's pivot-block inverse times the broadcast vector)
+template <int BS>
+__device__ __forceinline__ double row_dot(const double *__restrict__ Mrow, const double *__restrict__ v, int bs) {
+    if (BS > 0) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        ix.col[s] = (lane < bs && s < S.ow) ? (int)S.off_col[((size_t)t * bs + lane) * S.ow + s] : -1;
-        const bool okT = lane < bs && s < S.owT;
-        ix.trow[s] = okT ? (int)S.offT_row[((size_t)t * bs + lane) * S.owT + s] : -1;
-        ix.tslot[s] = okT ? (int)S.offT_slot[((size_t)t * bs + lane) * S.owT + s] : 0;
+        for (int c = 0; c < BS; c += 2) {
+            const double2 m = *reinterpret_cast<const double2 *>(Mrow + c);
+            const double2 w = *reinterpret_cast<const double2 *>(v + c);
+            if ((c >> 1) & 1) {
+                a2 = fma(m.x, w.x, a2);
+                a3 = fma(m.y, w.y, a3);
+            } else {
+                a0 = fma(m.x, w.x, a0);
+                a1 = fma(m.y, w.y, a1);
+            }
+        }
+        return (a0 + a1) + (a2 + a3);
+    } else {
+        double a0 = 0.0;
+        for (int c = 0; c < bs; ++c) a0 = fma(Mrow[c], v[c], a0);
+        return a0;
     }
 }
-// sum_s Off_t[lane][s] * v[col]   (rows of block t+1 from a vector over block t)
-__device__ __forceinline__ double off_mul(const DevSym &S, const double *__restrict__ sOff, int t, double v, int lane, int bs,
-                                          const OffIdx &ix, bool cached) {
+// sum_s Off_t[lane][s] * src[col]: rows of stage t+1 from a vector over stage t (lane < bs)
+__device__ __forceinline__ double off_mul(const SolverCtx &C, int t, const double *__restrict__ src, int lane) {
     double acc = 0.0;
-    if (cached) {
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int a = ix.col[s];
-            const double up = __shfl_sync(0xffffffffu, v, a >= 0 ? a : 0);
-            if (a >= 0) acc = fma(sOff[((size_t)t * bs + lane) * S.ow + s], up, acc);
-        }
-    } else {
-        for (int s = 0; s < S.ow; ++s) {
-            const int a = lane < bs ? (int)S.off_col[((size_t)t * bs + lane) * S.ow + s] : -1;
-            const double up = __shfl_sync(0xffffffffu, v, a >= 0 ? a : 0);
-            if (a >= 0) acc = fma(sOff[((size_t)t * bs + lane) * S.ow + s], up, acc);
-        }
+    const int base = (t * C.bs + lane) * C.ow;
+    for (int s = 0; s < C.ow; ++s) {
+        const int a = C.offCol()[base + s];
+        if (a >= 0) acc = fma(C.off()[base + s], src[a], acc);
     }
     return acc;
 }
-// Off_t' * v: (columns of block t from a vector over block t+1)
-__device__ __forceinline__ double offT_mul(const DevSym &S, const double *__restrict__ sOff, int t, double v, int lane, int bs,
-                                           const OffIdx &ix, bool cached) {
+// (Off_t' src)[lane]: columns of stage t from a vector over stage t+1 (lane < bs)
+__device__ __forceinline__ double offT_mul(const SolverCtx &C, int t, const double *__restrict__ src, int lane) {
     double acc = 0.0;
-    const double *blk = sOff + (size_t)t * bs * S.ow;
-    if (cached) {
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int r = ix.trow[s];
-            const double up = __shfl_sync(0xffffffffu, v, r >= 0 ? r : 0);
-            if (r >= 0) acc = fma(blk[ix.tslot[s]], up, acc);
-        }
-    } else {
-        for (int s = 0; s < S.owT; ++s) {
-            const int r = lane < bs ? (int)S.offT_row[((size_t)t * bs + lane) * S.owT + s] : -1;
-            const int slot = lane < bs ? (int)S.offT_slot[((size_t)t * bs + lane) * S.owT + s] : 0;
-            const double up = __shfl_sync(0xffffffffu, v, r >= 0 ? r : 0);
-            if (r >= 0) acc = fma(blk[slot], up, acc);
-        }
+    const int base = (t * C.bs + lane) * C.owT;
+    const double *blk = C.off() + (size_t)t * C.bs * C.ow;
+    for (int s = 0; s < C.owT; ++s) {
+        const int r = C.offTrow()[base + s];
+        if (r >= 0) acc = fma(blk[C.offTslot()[base + s]], src[r], acc);
     }
     return acc;
+}
+// one substitution step: returns (Dinv_t * yv)[lane]  (yv distributed one entry per lane)
+template <int BS>
+__device__ __forceinline__ double apply_dinv(const SolverCtx &C, int t, double yv, int lane) {
+    const int bs = BS > 0 ? BS : C.bs;
+    if (lane < bs) C.vbuf()[lane] = yv;
+    __syncwarp();
+    const int rl = lane < bs ? lane : bs - 1;
+    const double u = row_dot<BS>(C.dinv() + ((size_t)t * bs + rl) * bs, C.vbuf(), bs);
+    __syncwarp();
+    return u;
 }
 
-__device__ __forceinline__ double dinv_at(const double *Dt, int r, int c) {
-    return r >= c ? Dt[r * (r + 1) / 2 + c] : Dt[c * (c + 1) / 2 + r];
-}
-// D_t -= Off_{t-1} Dinv_{t-1} Off_{t-1}'  (above = true)   or   D_t -= Off_t' Dinv_{t+1} Off_t  (above = false); one warp
-static __device__ __noinline__ void schur_update(const DevSym &S, double *sDinv, const double *sOff, int t, int lane, int bs, bool above) {
-    const int dpb = S.dpb;
-    if (above) {
-        const int ow = S.ow;
-        const double *Dp = sDinv + (size_t)(t - 1) * dpb;
-        for (int e = lane; e < dpb; e += 32) {
-            const int rc = S.tri_rc[e], r = rc >> 8, c = rc & 0xFF;
-            double acc = 0.0;
-            for (int s = 0; s < ow; ++s) {
-                const int a = S.off_col[((size_t)(t - 1) * bs + r) * ow + s];
-                if (a < 0) continue;
-                const double va = sOff[((size_t)(t - 1) * bs + r) * ow + s];
-                for (int s2 = 0; s2 < ow; ++s2) {
-                    const int b = S.off_col[((size_t)(t - 1) * bs + c) * ow + s2];
-                    if (b < 0) continue;
-                    acc += va * dinv_at(Dp, a, b) * sOff[((size_t)(t - 1) * bs + c) * ow + s2];
-                }
-            }
-            sDinv[(size_t)t * dpb + e] -= acc;
-        }
-    } else {
-        const int owT = S.owT;
-        const double *Dn = sDinv + (size_t)(t + 1) * dpb;
-        const double *blk = sOff + (size_t)t * bs * S.ow;
-        for (int e = lane; e < dpb; e += 32) {
-            const int rc = S.tri_rc[e], r = rc >> 8, c = rc & 0xFF;
-            double acc = 0.0;
-            for (int s = 0; s < owT; ++s) {
-                const int a = S.offT_row[((size_t)t * bs + r) * owT + s];
-                if (a < 0) continue;
-                const double va = blk[S.offT_slot[((size_t)t * bs + r) * owT + s]];
-                for (int s2 = 0; s2 < owT; ++s2) {
-                    const int b = S.offT_row[((size_t)t * bs + c) * owT + s2];
-                    if (b < 0) continue;
-                    acc += va * dinv_at(Dn, a, b) * blk[S.offT_slot[((size_t)t * bs + c) * owT + s2]];
-                }
-            }
-            sDinv[(size_t)t * dpb + e] -= acc;
-        }
-    }
-    __syncwarp();
-}
-// In-place inverse of the packed SPD block M (one warp, Gauss-Jordan without pivoting on a full
-// bs x bs scratch copy F; all 32 lanes sweep the bs*bs entries of each elimination step).
-static __device__ __noinline__ void invert_block(const DevSym &S, double *M, double *F, int lane, int bs) {
-    const int dpb = S.dpb;
-    for (int e = lane; e < dpb; e += 32) {
-        const int rc = S.tri_rc[e], r = rc >> 8, c = rc & 0xFF;
-        const double v = M[e];
-        F[r * bs + c] = v;
-        F[c * bs + r] = v;
-    }
-    __syncwarp();
+// Pivot block of stage t: D_t = S_tt - (neighbour update), inverted in place in shared memory.
+//   mode bit 1: minus Off_{t-1} Dinv_{t-1} Off_{t-1}';  mode bit 2: minus Off_t' Dinv_{t+1} Off_t
+//   (both at the middle stage).
+// One warp; all 32 lanes sweep the bs*bs entries.  Deliberately compact (runtime loops, not inlined):
+// a fully unrolled register version stalls on instruction fetch -- one warp cannot hide I-cache misses.
+template <int BS>
+static __device__ __noinline__ void factor_block(const SolverCtx &C, int t, int mode, int lane) {
+    const int bs = BS > 0 ? BS : C.bs;
     const int nn = bs * bs;
+    double *M = C.dinv() + (size_t)t * nn;
+#pragma unroll 1
+    for (int pass = 1; pass <= 2; ++pass) {
+        if (!(mode & pass)) continue;
+        const bool above = pass == 1;
+        const int tb = above ? t - 1 : t; // off-diagonal block involved
+        const double *Dn = C.dinv() + (size_t)(above ? t - 1 : t + 1) * nn;
+        const double *blk = C.off() + (size_t)tb * bs * C.ow;
+        const int cnt = above ? C.ow : C.owT;
+#pragma unroll 1
+        for (int e = lane; e < nn; e += 32) {
+            const int r = e / bs, c = e - r * bs;
+            double acc = 0.0;
+            for (int s = 0; s < cnt; ++s) {
+                int a;
+                double va = 0.0;
+                if (above) {
+                    a = C.offCol()[(tb * bs + r) * C.ow + s];
+                    if (a >= 0) va = blk[r * C.ow + s];
+                } else {
+                    a = C.offTrow()[(tb * bs + r) * C.owT + s];
+                    if (a >= 0) va = blk[C.offTslot()[(tb * bs + r) * C.owT + s]];
+                }
+                if (a < 0) continue;
+                for (int s2 = 0; s2 < cnt; ++s2) {
+                    int b2;
+                    double vb = 0.0;
+                    if (above) {
+                        b2 = C.offCol()[(tb * bs + c) * C.ow + s2];
+                        if (b2 >= 0) vb = blk[c * C.ow + s2];
+                    } else {
+                        b2 = C.offTrow()[(tb * bs + c) * C.owT + s2];
+                        if (b2 >= 0) vb = blk[C.offTslot()[(tb * bs + c) * C.owT + s2]];
+                    }
+                    if (b2 >= 0) acc += va * Dn[a * bs + b2] * vb;
+                }
+            }
+            M[e] -= acc;
+        }
+        __syncwarp();
+    }
+    // Gauss-Jordan without pivoting (SPD block).  The reciprocal of the next pivot is started as soon as
+    // the trailing update of step k is visible, so the division overlaps the row/column fix-up of step k.
+    double pinv = 1.0 / M[0];
+#pragma unroll 1
     for (int k = 0; k < bs; ++k) {
-        const double pinv = 1.0 / F[k * bs + k];
+        const double *rowk = M + k * bs;
+#pragma unroll 1
         for (int e = lane; e < nn; e += 32) {
             const int i = e / bs, j = e - i * bs;
-            if (i != k && j != k) F[e] = fma(-(F[i * bs + k] * pinv), F[k * bs + j], F[e]);
+            if (i != k && j != k) M[e] = fma(-(M[i * bs + k] * pinv), rowk[j], M[e]);
         }
         __syncwarp();
-        for (int e = lane; e < bs; e += 32) {
-            if (e != k) {
-                F[e * bs + k] = -(F[e * bs + k] * pinv);
-                F[k * bs + e] *= pinv;
+        const double pnext = k + 1 < bs ? 1.0 / M[(k + 1) * bs + k + 1] : 0.0;
+        if (lane < bs) {
+            if (lane != k) {
+                M[lane * bs + k] = -(M[lane * bs + k] * pinv);
+                M[k * bs + lane] *= pinv;
             } else {
-                F[k * bs + k] = pinv;
+                M[k * bs + k] = pinv;
             }
         }
+        pinv = pnext;
         __syncwarp();
     }
-    for (int e = lane; e < dpb; e += 32) {
-        const int rc = S.tri_rc[e];
-        M[e] = F[(rc >> 8) * bs + (rc & 0xFF)];
+}
+
+// ---- software-pipelined substitution step (fast path: compile-time block size, <= 2 off-diagonal
+// entries per block row/column).  Everything that does not depend on the previous stage's result --
+// the lane's row of the inverted pivot block, its right-hand side entry, the off-diagonal values and
+// indices -- is fetched into registers one step ahead; the dependent part is: two gathers from the
+// previous stage, two FMAs, one shared-memory broadcast of the block vector, 2N FMAs.
+template <int BS>
+struct StepRegs {
+    double m[BS > 0 ? BS : 2];
+    double b, ov0, ov1;
+    int oi0, oi1;
+};
+// tb < 0: no off-diagonal part.  transposed: use Off_tb' (columns of stage tb from stage tb+1).
+template <int BS>
+__device__ __forceinline__ void chain_prefetch(const SolverCtx &C, int t, int tb, bool transposed, int lane, StepRegs<BS> &P) {
+    constexpr int NB = BS > 0 ? BS : 2;
+    const int rl = lane < NB ? lane : NB - 1;
+    const double *row = C.dinv() + ((size_t)t * NB + rl) * NB;
+#pragma unroll
+    for (int c = 0; c < NB; c += 2) {
+        const double2 d = *reinterpret_cast<const double2 *>(row + c);
+        P.m[c] = d.x;
+        P.m[c + 1] = d.y;
     }
+    P.b = C.rhs()[t * NB + rl];
+    int a0 = -1, a1 = -1;
+    double v0 = 0.0, v1 = 0.0;
+    if (tb >= 0) {
+        if (!transposed) {
+            const int base = (tb * NB + rl) * C.ow;
+            a0 = C.offCol()[base];
+            v0 = C.off()[base];
+            if (C.ow > 1) {
+                a1 = C.offCol()[base + 1];
+                v1 = C.off()[base + 1];
+            }
+        } else {
+            const int base = (tb * NB + rl) * C.owT;
+            const double *blk = C.off() + (size_t)tb * NB * C.ow;
+            a0 = C.offTrow()[base];
+            v0 = blk[C.offTslot()[base]];
+            if (C.owT > 1) {
+                a1 = C.offTrow()[base + 1];
+                v1 = blk[C.offTslot()[base + 1]];
+            }
+        }
+    }
+    P.oi0 = a0 >= 0 ? a0 : 0;
+    P.ov0 = a0 >= 0 ? v0 : 0.0;
+    P.oi1 = a1 >= 0 ? a1 : 0;
+    P.ov1 = a1 >= 0 ? v1 : 0.0;
+}
+// fwd:  rhs_t <- Dinv_t (b - off . src)        bwd:  rhs_t <- b - Dinv_t (off . src)
+template <int BS>
+__device__ __forceinline__ void chain_apply(const SolverCtx &C, int t, int src_stage, bool fwd, int lane, const StepRegs<BS> &P) {
+    constexpr int NB = BS > 0 ? BS : 2;
+    const double *src = C.rhs() + src_stage * NB;
+    const double off = fma(P.ov0, src[P.oi0], P.ov1 * src[P.oi1]);
+    const double v = fwd ? P.b - off : off;
+    if (lane < NB) C.vbuf()[lane] = v;
     __syncwarp();
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int c = 0; c < NB; c += 2) {
+        const double2 w = *reinterpret_cast<const double2 *>(C.vbuf() + c);
+        if ((c >> 1) & 1) {
+            a2 = fma(P.m[c], w.x, a2);
+            a3 = fma(P.m[c + 1], w.y, a3);
+        } else {
+            a0 = fma(P.m[c], w.x, a0);
+            a1 = fma(P.m[c + 1], w.y, a1);
+        }
+    }
+    const double acc = (a0 + a1) + (a2 + a3);
+    if (lane < NB) C.rhs()[t * NB + lane] = fwd ? acc : P.b - acc;
+    __syncwarp();
+}
+
+template <int BS>
+__device__ __forceinline__ void chain_step(const SolverCtx &C, int t, int tb, bool transposed, int src_stage, bool fwd, int lane) {
+    StepRegs<BS> P;
+    chain_prefetch<BS>(C, t, tb, transposed, lane, P);
+    chain_apply<BS>(C, t, src_stage, fwd, lane, P);
 }
 
 // ================================================================================================
 //                                        the ADMM kernel
 // ================================================================================================
-#define ROWS_LOOP(j, i) _Pragma("unroll") for (int j = 0, i = tid; j < RPT; ++j, i += NT) if (i < mu)
-#define COLS_LOOP(c, p) _Pragma("unroll") for (int c = 0, p = tid; c < CPT; ++c, p += NT) if (p < np)
+// phase timers: thread 0 accumulates clock64() deltas per phase when B.prof is set
+enum { PH_LOAD = 0, PH_SCALE, PH_FACTOR, PH_RHS, PH_SOLVE, PH_UPDATE, PH_INFO, PH_STORE, PH_ASSEMBLE, PH_COUNT };
+#define PHASE_MARK(ph)                                                              \
+    do {                                                                            \
+        if (B.prof != nullptr && tid == kSolverThreads) {                           \
+            const long long now__ = clock64();                                      \
+            atomicAdd(&B.prof[ph], (unsigned long long)(now__ - t_phase));          \
+            t_phase = now__;                                                        \
+        }                                                                           \
+    } while (0)
 
-template <int NT, int RPT, int CPT, int BS>
-__global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const DevBatch B, const DevSettings st) {
-    extern __shared__ __align__(16) double smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#define ROWS_LOOP(j, i) _Pragma("unroll") for (int j = 0, i = oid; j < RPT; ++j, i += kOwners) if (i < mu)
+#define COLS_LOOP(c, p) _Pragma("unroll") for (int c = 0, p = oid; c < CPT; ++c, p += kOwners) if (p < np)
+// for every entry e = (pos << 16 | k) of compact row i
+#define ROW_ENTRIES(i, e) \
+    for (int q__ = sRowPtr[i], q1__ = sRowPtr[(i) + 1]; q__ < q1__; ++q__) \
+        if (const uint32_t e = sRowEnt[q__]; true)
+// for every CSC value index k of the variable at position p
+#define COL_ENTRIES(p, k) for (int k = (int)(sColRange[p] >> 8), k1__ = k + (int)(sColRange[p] & 0xFFu); k < k1__; ++k)
+// for every entry e = (other_pos << 16 | kPu) of the full-symmetric P at position p
+#define PF_ENTRIES(p, e) \
+    for (int q__ = sPfPtr[p], q1__ = sPfPtr[(p) + 1]; q__ < q1__; ++q__) \
+        if (const uint32_t e = sPfEnt[q__]; true)
+
+// ---- cooperative block factorisation -----------------------------------------------------------------
+// The two elimination chains (stages 0..h-1 downwards, T-1..h+1 upwards) are sequential over stages, and
+// inverting one pivot block is sequential over its bs pivots; a single warp spends ~10 cycles per
+// dependent instruction on that.  So each chain is run by a GROUP of 7 warps (224 threads) in which every
+// thread owns matrix entries in registers: per pivot step the owners of row k and column k publish them
+// to shared memory, one named barrier, every thread updates its own entries.  Critical path per pivot:
+// publish -> barrier -> 3 shared loads -> reciprocal -> 2 FMAs.
+constexpr int kFactorGroup = 224; // threads per chain group (warps 0-6: top chain, warps 7-13: bottom chain)
+
+template <int BS>
+static __device__ __noinline__ void factor_block_group(const DevSym &S, unsigned char *smem_raw, int t, int mode, int g, int gl) {
     const int bs = BS > 0 ? BS : S.bs;
-    const int T = S.T, np = S.n_pad, mu = S.m_used, dpb = S.dpb, h = S.T / 2;
-    double *const sA = smem + S.oA;
-    double *const sP = smem + S.oP;
-    double *const sW = smem + S.oW;
-    double *const sRHS = smem + S.oRHS;
-    double *const sDinv = smem + S.oDinv;
-    double *const sOff = smem + S.oOff;
-    double *const sInv = smem + S.oInv;
-    double *const sRed = smem + S.oRed;
-    uint64_t *const sBar = reinterpret_cast<uint64_t *>(smem + S.oEnd);
-    int *const sWork = reinterpret_cast<int *>(smem + S.oEnd + 1);
+    const int nn = bs * bs;
+    constexpr int EPL = BS > 0 ? (BS * BS + kFactorGroup - 1) / kFactorGroup : 5; // entries per thread (bs <= 32)
+    double *const Dall = reinterpret_cast<double *>(smem_raw + S.oDinv);
+    const double *const Offall = reinterpret_cast<const double *>(smem_raw + S.oOff);
+    const int8_t *const offCol = reinterpret_cast<const int8_t *>(smem_raw + S.oOffCol);
+    const int8_t *const offTrow = reinterpret_cast<const int8_t *>(smem_raw + S.oOffTrow);
+    const uint16_t *const offTslot = reinterpret_cast<const uint16_t *>(smem_raw + S.oOffTslot);
+    double *const pub = reinterpret_cast<double *>(smem_raw + S.oScr) + g * 128; // [parity][row k (32) | column k (32)]
+    double *M = Dall + (size_t)t * nn;
+    double val[EPL];
+    int ri[EPL], ci[EPL];
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) {
+        const int e = gl + q * kFactorGroup;
+        ri[q] = e < nn ? e / bs : -1;
+        ci[q] = e < nn ? e - ri[q] * bs : -1;
+        val[q] = e < nn ? M[e] : 0.0;
+    }
+    // neighbour updates: minus Off_{t-1} Dinv_{t-1} Off_{t-1}' (mode bit 1), minus Off_t' Dinv_{t+1} Off_t (bit 2)
+#pragma unroll 1
+    for (int pass = 1; pass <= 2; ++pass) {
+        if (!(mode & pass)) continue;
+        const bool above = pass == 1;
+        const int tb = above ? t - 1 : t;
+        const double *Dn = Dall + (size_t)(above ? t - 1 : t + 1) * nn;
+        const double *blk = Offall + (size_t)tb * bs * S.ow;
+        const int cnt = above ? S.ow : S.owT;
+#pragma unroll
+        for (int q = 0; q < EPL; ++q) {
+            if (ri[q] < 0) continue;
+            const int r = ri[q], c = ci[q];
+            double acc = 0.0;
+            for (int s1 = 0; s1 < cnt; ++s1) {
+                int a;
+                double va = 0.0;
+                if (above) {
+                    a = offCol[(tb * bs + r) * S.ow + s1];
+                    if (a >= 0) va = blk[r * S.ow + s1];
+                } else {
+                    a = offTrow[(tb * bs + r) * S.owT + s1];
+                    if (a >= 0) va = blk[offTslot[(tb * bs + r) * S.owT + s1]];
+                }
+                if (a < 0) continue;
+                for (int s2 = 0; s2 < cnt; ++s2) {
+                    int b2;
+                    double vb = 0.0;
+                    if (above) {
+                        b2 = offCol[(tb * bs + c) * S.ow + s2];
+                        if (b2 >= 0) vb = blk[c * S.ow + s2];
+                    } else {
+                        b2 = offTrow[(tb * bs + c) * S.owT + s2];
+                        if (b2 >= 0) vb = blk[offTslot[(tb * bs + c) * S.owT + s2]];
+                    }
+                    if (b2 >= 0) acc += va * Dn[a * bs + b2] * vb;
+                }
+            }
+            val[q] -= acc;
+        }
+    }
+    // Gauss-Jordan without pivoting (SPD block), entries in registers
+#pragma unroll 1
+    for (int k = 0; k < bs; ++k) {
+        double *rowk = pub + (k & 1) * 64, *colk = rowk + 32;
+#pragma unroll
+        for (int q = 0; q < EPL; ++q) {
+            if (ri[q] == k) rowk[ci[q]] = val[q];
+            if (ci[q] == k) colk[ri[q]] = val[q];
+        }
+        named_bar_sync(4 + g, kFactorGroup);
+        const double pinv = 1.0 / rowk[k];
+#pragma unroll
+        for (int q = 0; q < EPL; ++q) {
+            const int i = ri[q], j = ci[q];
+            if (i < 0) continue;
+            if (i != k && j != k) val[q] = fma(-(colk[i] * pinv), rowk[j], val[q]);
+            else if (i == k && j != k) val[q] *= pinv;
+            else if (j == k && i != k) val[q] = -(val[q] * pinv);
+            else val[q] = pinv;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < EPL; ++q)
+        if (ri[q] >= 0) M[gl + q * kFactorGroup] = val[q];
+    named_bar_sync(4 + g, kFactorGroup); // the next stage of this chain reads the inverse just stored
+}
 
-    const bool small_off = S.ow <= 4 && S.owT <= 4; // pattern of a block row fits the per-lane cache
-    const bool cached_off = S.uniform_off && small_off;
-    const bool hasq = B.q != nullptr;
-    OffIdx oix;
-    load_off_idx(S, 0, lane, bs, oix); // valid for every block when the pattern is uniform (T >= 2)
+// phase 0: both chains (threads 0..447);  phase 1: the middle stage (group 0) after a CTA-wide barrier
+template <int BS>
+__device__ __forceinline__ void factor_cooperative(const DevSym &S, unsigned char *smem_raw, int tid, int phase) {
+    if (tid >= 2 * kFactorGroup) return;
+    const int g = tid / kFactorGroup, gl = tid - g * kFactorGroup;
+    const int T = S.T, h = S.T / 2;
+    if (phase == 0) {
+        if (g == 0) {
+#pragma unroll 1
+            for (int t = 0; t < h; ++t) factor_block_group<BS>(S, smem_raw, t, t > 0 ? 1 : 0, 0, gl);
+        } else {
+#pragma unroll 1
+            for (int t = T - 1; t > h; --t) factor_block_group<BS>(S, smem_raw, t, t < T - 1 ? 2 : 0, 1, gl);
+        }
+    } else if (g == 0) {
+        factor_block_group<BS>(S, smem_raw, h, (h > 0 ? 1 : 0) | (h < T - 1 ? 2 : 0), 0, gl);
+    }
+}
 
-    if (tid == 0) mbar_init(sBar, 1);
+// Assembly of S = P + sigma I + A' diag(rho) A into the full-row pivot blocks and the ELL
+// off-diagonal blocks; destination driven (deterministic, no atomics), every thread of the CTA helps.
+// sW holds rho per compact row.
+static __device__ __noinline__ void assemble_S(const DevSym &S, double sigma, const double *sW, const double *sA, const double *sP,
+                                               double *sDinv, double *sOff, int tid, int bs) {
+    const int dpb = bs * (bs + 1) / 2, ndiag = S.T * dpb, bb = bs * bs;
+    for (int e = tid; e < ndiag; e += kThreads) {
+        double acc = 0.0;
+        const uint32_t q1 = S.sd_ptr[e + 1];
+        for (uint32_t q = S.sd_ptr[e]; q < q1; ++q) {
+            const gomp::Contrib cn = S.sd_con[q];
+            acc += sW[cn.row] * sA[cn.k1] * sA[cn.k2];
+        }
+        const uint16_t pk = S.sd_pk[e];
+        if (pk != 0xFFFFu) acc += sP[pk];
+        const int kind = S.sd_kind[e];
+        if (kind == 1) acc += sigma;
+        else if (kind == 2) acc = 1.0;
+        const int t = e / dpb, rc = S.tri_rc[e - t * dpb], r = rc >> 8, c = rc & 0xFF;
+        sDinv[(size_t)t * bb + r * bs + c] = acc;
+        sDinv[(size_t)t * bb + c * bs + r] = acc;
+    }
+    for (int e = tid; e < S.noff; e += kThreads) {
+        double acc = 0.0;
+        const uint32_t q1 = S.so_ptr[e + 1];
+        for (uint32_t q = S.so_ptr[e]; q < q1; ++q) {
+            const gomp::Contrib cn = S.so_con[q];
+            acc += sW[cn.row] * sA[cn.k1] * sA[cn.k2];
+        }
+        const uint16_t pk = S.so_pk[e];
+        if (pk != 0xFFFFu) acc += sP[pk];
+        sOff[e] = acc;
+    }
+}
+
+// control word the owners publish for the solver warps before every CTA-wide rendezvous
+enum { CTRL_SOLVE = 0, CTRL_FACTOR = 1, CTRL_EXIT = 2 };
+
+template <int RPT, int CPT, int BS>
+__global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, const DevBatch B, const DevSettings st) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool owner = tid >= kSolverThreads;
+    const int oid = tid - kSolverThreads;
+    const int bs = BS > 0 ? BS : S.bs;
+    const int T = S.T, np = S.n_pad, mu = S.m_used, h = S.T / 2, bb = bs * bs;
+    // shared-memory regions: addressed as base + constant-bank offset, no pointer registers kept alive
+#define sA (reinterpret_cast<double *>(smem_raw + S.oA))
+#define sP (reinterpret_cast<double *>(smem_raw + S.oP))
+#define sW (reinterpret_cast<double *>(smem_raw + S.oW))
+#define sRHS (reinterpret_cast<double *>(smem_raw + S.oRHS))
+#define sDinv (reinterpret_cast<double *>(smem_raw + S.oDinv))
+#define sOff (reinterpret_cast<double *>(smem_raw + S.oOff))
+#define sRed (reinterpret_cast<double *>(smem_raw + S.oRed))
+#define sRowEnt (reinterpret_cast<uint32_t *>(smem_raw + S.oRowEnt))
+#define sColRange (reinterpret_cast<uint32_t *>(smem_raw + S.oColRange))
+#define sPfEnt (reinterpret_cast<uint32_t *>(smem_raw + S.oPfEnt))
+#define sPuIJ (reinterpret_cast<uint32_t *>(smem_raw + S.oPuIJ))
+#define sRowPtr (reinterpret_cast<uint16_t *>(smem_raw + S.oRowPtr))
+#define sCscRow (reinterpret_cast<uint16_t *>(smem_raw + S.oCscRow))
+#define sPfPtr (reinterpret_cast<uint16_t *>(smem_raw + S.oPfPtr))
+#define sOffTslot (reinterpret_cast<uint16_t *>(smem_raw + S.oOffTslot))
+#define sOffCol (reinterpret_cast<int8_t *>(smem_raw + S.oOffCol))
+#define sOffTrow (reinterpret_cast<int8_t *>(smem_raw + S.oOffTrow))
+#define sBar (reinterpret_cast<uint64_t *>(smem_raw + S.oBar))
+#define sWork (reinterpret_cast<int *>(smem_raw + S.oBar + 8))
+#define sCtrl (reinterpret_cast<volatile int *>(smem_raw + S.oBar + 12))
+
+    // ---- once per kernel: sparsity pattern -> shared memory (identical for every QP of the batch)
+    for (int k = tid; k < S.nnzA; k += kThreads) {
+        sRowEnt[k] = S.row_csr[k];
+        sCscRow[k] = S.csc_row[k];
+    }
+    for (int k = tid; k < np; k += kThreads) sColRange[k] = S.col_range[k];
+    for (int k = tid; k <= mu; k += kThreads) sRowPtr[k] = S.row_ptr[k];
+    for (int k = tid; k < S.npf; k += kThreads) sPfEnt[k] = S.pf_csr[k];
+    for (int k = tid; k <= np; k += kThreads) sPfPtr[k] = S.pf_ptr[k];
+    for (int k = tid; k < S.nnzPu; k += kThreads) sPuIJ[k] = S.Pu_ij[k];
+    for (int k = tid; k < (T - 1) * bs * S.ow; k += kThreads) sOffCol[k] = S.off_col[k];
+    for (int k = tid; k < (T - 1) * bs * S.owT; k += kThreads) {
+        sOffTrow[k] = S.offT_row[k];
+        sOffTslot[k] = S.offT_slot[k];
+    }
+    if (tid == kSolverThreads) mbar_init(sBar, 1);
     uint32_t bar_phase = 0;
     __syncthreads();
 
     for (;;) {
-        if (tid == 0) *sWork = atomicAdd(B.work_counter, 1);
+        if (tid == kSolverThreads) *sWork = atomicAdd(B.work_counter, 1);
         __syncthreads();
         const int b = *sWork;
         if (b >= B.batch) break;
+
+        if (!owner) {
+            // =====================================================================================
+            // SOLVER warps: wait for the owners' control word, then factor or substitute.
+            // =====================================================================================
+            SolverCtx C;
+            C.sm = smem_u32(smem_raw);
+            C.oDinv = S.oDinv; C.oOff = S.oOff; C.oRHS = S.oRHS;
+            C.oV = S.oV + warp * 256; C.oScr = S.oScr + warp * bb * 8;
+            C.oOffCol = S.oOffCol; C.oOffTrow = S.oOffTrow; C.oOffTslot = S.oOffTslot;
+            C.bs = bs; C.T = T; C.ow = S.ow; C.owT = S.owT;
+            for (;;) {
+                __syncthreads(); // (E) control word + inputs published
+                const int ctrl = *sCtrl;
+                if (ctrl == CTRL_EXIT) break;
+                if (ctrl == CTRL_FACTOR) {
+                    assemble_S(S, st.sigma, sW, sA, sP, sDinv, sOff, tid, bs);
+                    __syncthreads(); // (B) S assembled
+                    factor_cooperative<BS>(S, smem_raw, tid, 0);
+                    __syncthreads(); // (C) both halves eliminated
+                    factor_cooperative<BS>(S, smem_raw, tid, 1);
+                    __syncthreads(); // (D) factor complete
+                    continue;
+                }
+                // block-tridiagonal solve, in place on sRHS
+                if (BS > 0 && S.ow <= 2 && S.owT <= 2) {
+                    // ---- fast path: per step, everything independent of the previous stage is loaded first
+                    if (warp == 0) { // stages 0 .. h-1 forward, the middle stage, then back up
+#pragma unroll 1
+                        for (int t = 0; t < h; ++t) chain_step<BS>(C, t, t - 1, false, t > 0 ? t - 1 : 0, true, lane);
+                        named_bar_sync(1, 64);
+                        double yv = lane < bs ? sRHS[h * bs + lane] : 0.0;
+                        if (lane < bs) {
+                            if (h > 0) yv -= off_mul(C, h - 1, sRHS + (h - 1) * bs, lane);
+                            if (h < T - 1) yv -= offT_mul(C, h, sRHS + (h + 1) * bs, lane);
+                        }
+                        const double xm = apply_dinv<BS>(C, h, yv, lane);
+                        if (lane < bs) sRHS[h * bs + lane] = xm;
+                        named_bar_sync(2, 64);
+#pragma unroll 1
+                        for (int t = h - 1; t >= 0; --t) chain_step<BS>(C, t, t, true, t + 1, false, lane); // x_t = u_t - Dinv_t Off_t' x_{t+1}
+                    } else { // stages T-1 .. h+1 forward (upwards), then back down
+#pragma unroll 1
+                        for (int t = T - 1; t > h; --t) chain_step<BS>(C, t, t < T - 1 ? t : -1, true, t < T - 1 ? t + 1 : t, true, lane);
+                        named_bar_sync(1, 64);
+                        named_bar_sync(2, 64);
+#pragma unroll 1
+                        for (int t = h + 1; t < T; ++t) chain_step<BS>(C, t, t - 1, false, t - 1, false, lane); // x_t = u_t - Dinv_t Off_{t-1} x_{t-1}
+                    }
+                } else
+                if (warp == 0) { // stages 0 .. h-1 forward, the middle stage, then back up
+                    for (int t = 0; t < h; ++t) {
+                        double yv = lane < bs ? sRHS[t * bs + lane] : 0.0;
+                        if (t > 0 && lane < bs) yv -= off_mul(C, t - 1, sRHS + (t - 1) * bs, lane);
+                        const double u = apply_dinv<BS>(C, t, yv, lane);
+                        if (lane < bs) sRHS[t * bs + lane] = u;
+                        __syncwarp();
+                    }
+                    named_bar_sync(1, 64);
+                    double yv = lane < bs ? sRHS[h * bs + lane] : 0.0;
+                    if (lane < bs) {
+                        if (h > 0) yv -= off_mul(C, h - 1, sRHS + (h - 1) * bs, lane);
+                        if (h < T - 1) yv -= offT_mul(C, h, sRHS + (h + 1) * bs, lane);
+                    }
+                    const double xm = apply_dinv<BS>(C, h, yv, lane);
+                    if (lane < bs) sRHS[h * bs + lane] = xm;
+                    named_bar_sync(2, 64);
+                    for (int t = h - 1; t >= 0; --t) { // x_t = u_t - Dinv_t Off_t' x_{t+1}
+                        const double v = lane < bs ? offT_mul(C, t, sRHS + (t + 1) * bs, lane) : 0.0;
+                        const double corr = apply_dinv<BS>(C, t, v, lane);
+                        if (lane < bs) sRHS[t * bs + lane] -= corr;
+                        __syncwarp();
+                    }
+                } else { // stages T-1 .. h+1 forward (upwards), then back down
+                    for (int t = T - 1; t > h; --t) {
+                        double yv = lane < bs ? sRHS[t * bs + lane] : 0.0;
+                        if (t < T - 1 && lane < bs) yv -= offT_mul(C, t, sRHS + (t + 1) * bs, lane);
+                        const double u = apply_dinv<BS>(C, t, yv, lane);
+                        if (lane < bs) sRHS[t * bs + lane] = u;
+                        __syncwarp();
+                    }
+                    named_bar_sync(1, 64);
+                    named_bar_sync(2, 64);
+                    for (int t = h + 1; t < T; ++t) { // x_t = u_t - Dinv_t Off_{t-1} x_{t-1}
+                        const double v = lane < bs ? off_mul(C, t - 1, sRHS + (t - 1) * bs, lane) : 0.0;
+                        const double corr = apply_dinv<BS>(C, t, v, lane);
+                        if (lane < bs) sRHS[t * bs + lane] -= corr;
+                        __syncwarp();
+                    }
+                }
+                __syncthreads(); // (F) x~ ready
+            }
+            fence_proxy_async();
+            continue;
+        }
+
+        // =========================================================================================
+        // OWNER warps: everything else.
+        // =========================================================================================
         const size_t bmu = (size_t)b * mu, bnp = (size_t)b * np;
+        const bool hasq = B.q != nullptr;
+        long long t_phase = clock64();
 
         // ------------------------------------------------------------------ load
         const double *gA = B.A_val + (size_t)b * B.A_pitch;
         if (B.bulk_ok) {
-            if (tid == 0) {
+            if (oid == 0) {
                 mbar_expect_tx(sBar, (uint32_t)S.nnzA * 8u);
                 bulk_g2s(sA, gA, (uint32_t)S.nnzA * 8u, sBar);
             }
         } else {
-            for (int k = tid; k < S.nnzA; k += NT) sA[k] = gA[k];
+            for (int k = oid; k < S.nnzA; k += kOwners) sA[k] = gA[k];
         }
-        for (int k = tid; k < S.nnzPu; k += NT) sP[k] = S.Pu_val[k];
+        for (int k = oid; k < S.nnzPu; k += kOwners) sP[k] = S.Pu_val[k];
         const double *gl = B.l + (size_t)b * S.m, *gu = B.u + (size_t)b * S.m;
         double z[RPT], y[RPT], lo[RPT], hi[RPT];
         double x[CPT];
@@ -367,10 +745,10 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
             lo[j] = fmax(gl[orig], -kInfty); // osqp-cpp clips bounds to +-OSQP_INFTY
             hi[j] = fmin(gu[orig], kInfty);
         }
-        int bad = 0;
-        for (int e = tid; e < S.n_empty; e += NT) {
+        double bad[1] = {0.0};
+        for (int e = oid; e < S.n_empty; e += kOwners) {
             const int r = S.empty_rows[e];
-            if (!(gl[r] <= 0.0 && 0.0 <= gu[r])) bad = 1;
+            if (!(gl[r] <= 0.0 && 0.0 <= gu[r])) bad[0] = 1.0;
         }
         if (B.bulk_ok) {
             unsigned spins = 0;
@@ -379,7 +757,9 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
             }
             bar_phase ^= 1;
         }
-        const int empty_infeasible = __syncthreads_or(bad);
+        owners_max<1>(bad, sRed, oid);
+        const bool empty_infeasible = bad[0] != 0.0;
+        PHASE_MARK(PH_LOAD);
 
         // ------------------------------------------------------------------ Ruiz equilibration
         double cscale = 1.0;
@@ -396,50 +776,44 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
                 double dt[CPT], et[RPT];
                 COLS_LOOP(c, p) {
                     double nrm = 0.0;
-                    const int pl = S.pf_len[p];
-                    for (int j = 0; j < pl; ++j) nrm = fmax(nrm, fabs(sP[S.pf_ent[(size_t)j * np + p] & 0xFFFFu]));
-                    const int cl = S.col_len[p], cs = S.col_start[p];
-                    for (int j = 0; j < cl; ++j) nrm = fmax(nrm, fabs(sA[cs + j]));
+                    PF_ENTRIES(p, e) nrm = fmax(nrm, fabs(sP[e & 0xFFFFu]));
+                    COL_ENTRIES(p, k) nrm = fmax(nrm, fabs(sA[k]));
                     dt[c] = 1.0 / sqrt(limit_scaling(nrm));
                     sRHS[p] = dt[c];
                 }
                 ROWS_LOOP(j, i) {
                     double nrm = 0.0;
-                    const int rl = S.row_len[i];
-                    for (int q = 0; q < rl; ++q) nrm = fmax(nrm, fabs(sA[S.row_ent[(size_t)q * mu + i] & 0xFFFFu]));
+                    ROW_ENTRIES(i, e) nrm = fmax(nrm, fabs(sA[e & 0xFFFFu]));
                     et[j] = 1.0 / sqrt(limit_scaling(nrm));
                 }
-                __syncthreads();
+                owners_sync();
                 ROWS_LOOP(j, i) {
-                    const int rl = S.row_len[i];
-                    for (int q = 0; q < rl; ++q) sA[S.row_ent[(size_t)q * mu + i] & 0xFFFFu] *= et[j];
+                    ROW_ENTRIES(i, e) sA[e & 0xFFFFu] *= et[j];
                     Ei[j] *= et[j];
                 }
-                for (int k = tid; k < S.nnzPu; k += NT) {
-                    const uint32_t ij = S.Pu_ij[k];
+                for (int k = oid; k < S.nnzPu; k += kOwners) {
+                    const uint32_t ij = sPuIJ[k];
                     sP[k] = (sP[k] * sRHS[ij >> 16]) * sRHS[ij & 0xFFFFu];
                 }
-                __syncthreads();
+                owners_sync();
                 double psum = 0.0, qn[1] = {0.0};
                 COLS_LOOP(c, p) {
-                    const int cl = S.col_len[p], cs = S.col_start[p];
-                    for (int j = 0; j < cl; ++j) sA[cs + j] *= dt[c];
+                    COL_ENTRIES(p, k) sA[k] *= dt[c];
                     qv[c] *= dt[c];
                     Dp[c] *= dt[c];
                     double nrm = 0.0;
-                    const int pl = S.pf_len[p];
-                    for (int j = 0; j < pl; ++j) nrm = fmax(nrm, fabs(sP[S.pf_ent[(size_t)j * np + p] & 0xFFFFu]));
+                    PF_ENTRIES(p, e) nrm = fmax(nrm, fabs(sP[e & 0xFFFFu]));
                     psum += nrm;
                     qn[0] = fmax(qn[0], fabs(qv[c]));
                 }
-                psum = block_sum<NT>(psum, sRed, tid);
-                block_max<1, NT>(qn, sRed, tid);
+                psum = owners_sum(psum, sRed, oid);
+                owners_max<1>(qn, sRed, oid);
                 double ct = fmax(psum / (double)S.n, limit_scaling(qn[0]));
                 ct = 1.0 / limit_scaling(ct);
-                for (int k = tid; k < S.nnzPu; k += NT) sP[k] *= ct;
+                for (int k = oid; k < S.nnzPu; k += kOwners) sP[k] *= ct;
                 COLS_LOOP(c, p) qv[c] *= ct;
                 cscale *= ct;
-                __syncthreads();
+                owners_sync();
             }
             ROWS_LOOP(j, i) {
                 lo[j] *= Ei[j];
@@ -453,6 +827,7 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
         }
         const double cinv = 1.0 / cscale;
         const bool uns = !st.scaled_termination;
+        PHASE_MARK(PH_SCALE);
 
         // ------------------------------------------------------------------ rho classification
         unsigned ctype = 0; // 2 bits per owned row: 0 inequality, 1 equality, 2 loose
@@ -464,7 +839,7 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
         }
 
         // ------------------------------------------------------------------ iterates
-        const int flags = B.flags[b];
+        const int flags = B.flag_bits;
         double rho;
         int rho_updates;
         if (flags & 1) {
@@ -487,17 +862,13 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
                 x[c] = var >= 0 ? (1.0 / B.Dg[bnp + p]) * B.x0[(size_t)b * S.n + var] : 0.0;
                 sRHS[p] = x[c];
             }
-            __syncthreads();
+            owners_sync();
             ROWS_LOOP(j, i) {
                 double acc = 0.0;
-                const int rl = S.row_len[i];
-                for (int q = 0; q < rl; ++q) {
-                    const uint32_t e = S.row_ent[(size_t)q * mu + i];
-                    acc = fma(sA[e & 0xFFFFu], sRHS[e >> 16], acc);
-                }
+                ROW_ENTRIES(i, e) acc = fma(sA[e & 0xFFFFu], sRHS[e >> 16], acc);
                 z[j] = acc;
             }
-            __syncthreads();
+            owners_sync();
         }
 
         double rho_eq = kRhoEqOverIneq * rho, rinv = 1.0 / rho, rinv_eq = 1.0 / rho_eq;
@@ -514,59 +885,23 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
 #pragma unroll 1
         for (int iter = 1; status == -10 && iter <= st.max_iter; ++iter) {
             if (need_factor) {
-                // ---------------- assemble S and factor it (two-way block elimination, explicit pivot inverses)
+                // ---------------- assemble S (all threads), then the solver warps factor it
                 ROWS_LOOP(j, i) {
                     const unsigned t = (ctype >> (2 * j)) & 3u;
                     sW[i] = RHO_OF(t);
                 }
-                __syncthreads();
-                const int ndiag = T * dpb;
-                for (int e = tid; e < ndiag; e += NT) {
-                    double acc = 0.0;
-                    const uint32_t q1 = S.sd_ptr[e + 1];
-                    for (uint32_t q = S.sd_ptr[e]; q < q1; ++q) {
-                        const gomp::Contrib cn = S.sd_con[q];
-                        acc += sW[cn.row] * sA[cn.k1] * sA[cn.k2];
-                    }
-                    const uint16_t pk = S.sd_pk[e];
-                    if (pk != 0xFFFFu) acc += sP[pk];
-                    const int kind = S.sd_kind[e];
-                    if (kind == 1) acc += st.sigma;
-                    else if (kind == 2) acc = 1.0;
-                    sDinv[e] = acc;
-                }
-                for (int e = tid; e < S.noff; e += NT) {
-                    double acc = 0.0;
-                    const uint32_t q1 = S.so_ptr[e + 1];
-                    for (uint32_t q = S.so_ptr[e]; q < q1; ++q) {
-                        const gomp::Contrib cn = S.so_con[q];
-                        acc += sW[cn.row] * sA[cn.k1] * sA[cn.k2];
-                    }
-                    const uint16_t pk = S.so_pk[e];
-                    if (pk != 0xFFFFu) acc += sP[pk];
-                    sOff[e] = acc;
-                }
-                __syncthreads();
-                if (warp == 0) {
-                    for (int t = 0; t < h; ++t) {
-                        if (t > 0) schur_update(S, sDinv, sOff, t, lane, bs, true);
-                        invert_block(S, sDinv + (size_t)t * dpb, sInv, lane, bs);
-                    }
-                } else if (warp == 1) {
-                    for (int t = T - 1; t > h; --t) {
-                        if (t < T - 1) schur_update(S, sDinv, sOff, t, lane, bs, false);
-                        invert_block(S, sDinv + (size_t)t * dpb, sInv + bs * bs, lane, bs);
-                    }
-                }
-                __syncthreads();
-                if (warp == 0) {
-                    if (h > 0) schur_update(S, sDinv, sOff, h, lane, bs, true);
-                    if (h < T - 1) schur_update(S, sDinv, sOff, h, lane, bs, false);
-                    invert_block(S, sDinv + (size_t)h * dpb, sInv, lane, bs);
-                }
-                __syncthreads();
+                if (oid == 0) *sCtrl = CTRL_FACTOR;
+                __syncthreads(); // (E)
+                assemble_S(S, st.sigma, sW, sA, sP, sDinv, sOff, tid, bs);
+                __syncthreads(); // (B)
+                PHASE_MARK(PH_ASSEMBLE);
+                factor_cooperative<BS>(S, smem_raw, tid, 0);
+                __syncthreads(); // (C)
+                factor_cooperative<BS>(S, smem_raw, tid, 1);
+                __syncthreads(); // (D)
                 need_factor = false;
                 w_dirty = true;
+                PHASE_MARK(PH_FACTOR);
             }
             if (w_dirty) {
                 ROWS_LOOP(j, i) {
@@ -574,73 +909,20 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
                     sW[i] = fma(RHO_OF(t), z[j], -y[j]);
                 }
                 w_dirty = false;
-                __syncthreads();
+                owners_sync();
             }
             // ---------------- rhs = sigma x - q + A'(rho z - y)
             COLS_LOOP(c, p) {
                 double acc = st.sigma * x[c];
                 if (hasq) acc -= B.qs[bnp + p];
-                const int cl = S.col_len[p], cs = S.col_start[p];
-                for (int j = 0; j < cl; ++j) acc = fma(sA[cs + j], sW[S.col_row[(size_t)j * np + p]], acc);
+                COL_ENTRIES(p, k) acc = fma(sA[k], sW[sCscRow[k]], acc);
                 sRHS[p] = acc;
             }
-            __syncthreads();
-            // ---------------- block-tridiagonal solve, in place on sRHS
-            if (warp == 0) { // top chain: blocks 0 .. h-1, then the middle block, then back up
-                double uprev = 0.0;
-                for (int t = 0; t < h; ++t) {
-                    double yv = lane < bs ? sRHS[t * bs + lane] : 0.0;
-                    if (t > 0) {
-                        if (small_off && !cached_off) load_off_idx(S, t - 1, lane, bs, oix);
-                        yv -= off_mul(S, sOff, t - 1, uprev, lane, bs, oix, small_off);
-                    }
-                    uprev = gemv_dinv<BS>(sDinv + (size_t)t * dpb, yv, lane, bs);
-                    if (lane < bs) sRHS[t * bs + lane] = uprev;
-                }
-                named_bar_sync(1, 64);
-                double yv = lane < bs ? sRHS[h * bs + lane] : 0.0;
-                if (h > 0) {
-                    if (small_off && !cached_off) load_off_idx(S, h - 1, lane, bs, oix);
-                    yv -= off_mul(S, sOff, h - 1, uprev, lane, bs, oix, small_off);
-                }
-                if (h < T - 1) {
-                    if (small_off && !cached_off) load_off_idx(S, h, lane, bs, oix);
-                    const double unext = lane < bs ? sRHS[(h + 1) * bs + lane] : 0.0;
-                    yv -= offT_mul(S, sOff, h, unext, lane, bs, oix, small_off);
-                }
-                double xn = gemv_dinv<BS>(sDinv + (size_t)h * dpb, yv, lane, bs);
-                if (lane < bs) sRHS[h * bs + lane] = xn;
-                named_bar_sync(2, 64);
-                for (int t = h - 1; t >= 0; --t) { // x_t = u_t - Dinv_t Off_t' x_{t+1}
-                    if (small_off && !cached_off) load_off_idx(S, t, lane, bs, oix);
-                    const double v = offT_mul(S, sOff, t, xn, lane, bs, oix, small_off);
-                    const double corr = gemv_dinv<BS>(sDinv + (size_t)t * dpb, v, lane, bs);
-                    xn = (lane < bs ? sRHS[t * bs + lane] : 0.0) - corr;
-                    if (lane < bs) sRHS[t * bs + lane] = xn;
-                }
-            } else if (warp == 1) { // bottom chain: blocks T-1 .. h+1, then back down
-                double unext = 0.0;
-                for (int t = T - 1; t > h; --t) {
-                    double yv = lane < bs ? sRHS[t * bs + lane] : 0.0;
-                    if (t < T - 1) {
-                        if (small_off && !cached_off) load_off_idx(S, t, lane, bs, oix);
-                        yv -= offT_mul(S, sOff, t, unext, lane, bs, oix, small_off);
-                    }
-                    unext = gemv_dinv<BS>(sDinv + (size_t)t * dpb, yv, lane, bs);
-                    if (lane < bs) sRHS[t * bs + lane] = unext;
-                }
-                named_bar_sync(1, 64);
-                named_bar_sync(2, 64);
-                double xp = lane < bs ? sRHS[h * bs + lane] : 0.0;
-                for (int t = h + 1; t < T; ++t) { // x_t = u_t - Dinv_t Off_{t-1} x_{t-1}
-                    if (small_off && !cached_off) load_off_idx(S, t - 1, lane, bs, oix);
-                    const double v = off_mul(S, sOff, t - 1, xp, lane, bs, oix, small_off);
-                    const double corr = gemv_dinv<BS>(sDinv + (size_t)t * dpb, v, lane, bs);
-                    xp = (lane < bs ? sRHS[t * bs + lane] : 0.0) - corr;
-                    if (lane < bs) sRHS[t * bs + lane] = xp;
-                }
-            }
-            __syncthreads();
+            if (oid == 0) *sCtrl = CTRL_SOLVE;
+            PHASE_MARK(PH_RHS);
+            __syncthreads(); // (E) rhs published; the solver warps substitute
+            __syncthreads(); // (F) x~ in sRHS
+            PHASE_MARK(PH_SOLVE);
 
             const bool last = iter == st.max_iter;
             const bool can_check = st.check_termination && (iter % st.check_termination == 0);
@@ -654,11 +936,7 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
             }
             ROWS_LOOP(j, i) {
                 double zt = 0.0;
-                const int rl = S.row_len[i];
-                for (int q = 0; q < rl; ++q) {
-                    const uint32_t e = S.row_ent[(size_t)q * mu + i];
-                    zt = fma(sA[e & 0xFFFFu], sRHS[e >> 16], zt);
-                }
+                ROW_ENTRIES(i, e) zt = fma(sA[e & 0xFFFFu], sRHS[e >> 16], zt);
                 const unsigned t = (ctype >> (2 * j)) & 3u;
                 const double zr = st.alpha * zt + (1.0 - st.alpha) * z[j];
                 const double zn = fmin(fmax(zr + RINV_OF(t) * y[j], lo[j]), hi[j]);
@@ -668,7 +946,8 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
                 sW[i] = fma(RHO_OF(t), zn, -y[j]); // w = rho z - y for the next gather
                 if (do_info) B.dyg[bmu + i] = d;
             }
-            __syncthreads(); // sRHS is overwritten by the next gather, which reads sW
+            owners_sync(); // sRHS is overwritten by the next gather, which reads sW
+            PHASE_MARK(PH_UPDATE);
 
             if (do_info) {
                 // ---------------- residuals and the norms OSQP's tolerances need (update_info)
@@ -676,16 +955,12 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
                 COLS_LOOP(c, p) sRHS[p] = x[c];
                 ROWS_LOOP(j, i) sW[i] = y[j];
                 w_dirty = true;
-                __syncthreads();
+                owners_sync();
 #pragma unroll
                 for (int k = 0; k < kRedK; ++k) nv[k] = 0.0;
                 ROWS_LOOP(j, i) {
                     double ax = 0.0;
-                    const int rl = S.row_len[i];
-                    for (int q = 0; q < rl; ++q) {
-                        const uint32_t e = S.row_ent[(size_t)q * mu + i];
-                        ax = fma(sA[e & 0xFFFFu], sRHS[e >> 16], ax);
-                    }
+                    ROW_ENTRIES(i, e) ax = fma(sA[e & 0xFFFFu], sRHS[e >> 16], ax);
                     const double pr = ax - z[j];
                     const double einv = 1.0 / B.Eg[bmu + i];
                     nv[0] = fmax(nv[0], fabs(einv * pr));
@@ -697,13 +972,8 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
                 }
                 COLS_LOOP(c, p) {
                     double px = 0.0, aty = 0.0;
-                    const int pl = S.pf_len[p];
-                    for (int j = 0; j < pl; ++j) {
-                        const uint32_t e = S.pf_ent[(size_t)j * np + p];
-                        px = fma(sP[e & 0xFFFFu], sRHS[e >> 16], px);
-                    }
-                    const int cl = S.col_len[p], cs = S.col_start[p];
-                    for (int j = 0; j < cl; ++j) aty = fma(sA[cs + j], sW[S.col_row[(size_t)j * np + p]], aty);
+                    PF_ENTRIES(p, e) px = fma(sP[e & 0xFFFFu], sRHS[e >> 16], px);
+                    COL_ENTRIES(p, k) aty = fma(sA[k], sW[sCscRow[k]], aty);
                     const double qq = hasq ? B.qs[bnp + p] : 0.0;
                     const double du = qq + px + aty;
                     const double dinv = 1.0 / B.Dg[bnp + p];
@@ -716,7 +986,7 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
                     nv[12] = fmax(nv[12], fabs(aty));
                     nv[13] = fmax(nv[13], fabs(qq));
                 }
-                block_max<kRedK, NT>(nv, sRed, tid);
+                owners_max<kRedK>(nv, sRed, oid);
                 pri_res = uns ? nv[0] : nv[1];
                 dua_res = uns ? cinv * nv[6] : nv[7];
                 iters_done = iter;
@@ -772,19 +1042,18 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
                             nrm[0] = fmax(nrm[0], fabs(uns ? B.Eg[bmu + i] * d : d));
                             lhs += hi[j] * fmax(d, 0.0) + lo[j] * fmin(d, 0.0);
                         }
-                        block_max<1, NT>(nrm, sRed, tid);
-                        lhs = block_sum<NT>(lhs, sRed, tid);
+                        owners_max<1>(nrm, sRed, oid);
+                        lhs = owners_sum(lhs, sRed, oid);
                         if (nrm[0] > kDivTol && lhs < -epi * nrm[0]) {
                             ROWS_LOOP(j, i) sW[i] = dyr[j];
-                            __syncthreads();
+                            owners_sync();
                             double v[1] = {0.0};
                             COLS_LOOP(c, p) {
                                 double acc = 0.0;
-                                const int cl = S.col_len[p], cs = S.col_start[p];
-                                for (int j = 0; j < cl; ++j) acc = fma(sA[cs + j], sW[S.col_row[(size_t)j * np + p]], acc);
+                                COL_ENTRIES(p, k) acc = fma(sA[k], sW[sCscRow[k]], acc);
                                 v[0] = fmax(v[0], fabs(uns ? (1.0 / B.Dg[bnp + p]) * acc : acc));
                             }
-                            block_max<1, NT>(v, sRed, tid);
+                            owners_max<1>(v, sRed, oid);
                             pic = v[0] < epi * nrm[0];
                         }
                     }
@@ -800,38 +1069,31 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
                             nrm[0] = fmax(nrm[0], fabs(uns ? B.Dg[bnp + p] * d : d));
                             qdx += B.qs[bnp + p] * d;
                         }
-                        block_max<1, NT>(nrm, sRed, tid);
-                        qdx = block_sum<NT>(qdx, sRed, tid);
+                        owners_max<1>(nrm, sRed, oid);
+                        qdx = owners_sum(qdx, sRed, oid);
                         const double cs_ = uns ? cscale : 1.0;
                         if (nrm[0] > kDivTol && qdx < -cs_ * edi * nrm[0]) {
                             COLS_LOOP(c, p) sRHS[p] = B.dxg[bnp + p];
-                            __syncthreads();
+                            owners_sync();
                             double v[1] = {0.0};
                             COLS_LOOP(c, p) {
                                 double acc = 0.0;
-                                const int pl = S.pf_len[p];
-                                for (int j = 0; j < pl; ++j) {
-                                    const uint32_t e = S.pf_ent[(size_t)j * np + p];
-                                    acc = fma(sP[e & 0xFFFFu], sRHS[e >> 16], acc);
-                                }
+                                PF_ENTRIES(p, e) acc = fma(sP[e & 0xFFFFu], sRHS[e >> 16], acc);
                                 v[0] = fmax(v[0], fabs(uns ? (1.0 / B.Dg[bnp + p]) * acc : acc));
                             }
-                            block_max<1, NT>(v, sRed, tid);
+                            owners_max<1>(v, sRed, oid);
                             if (v[0] < cs_ * edi * nrm[0]) {
-                                int viol = 0;
+                                double viol[1] = {0.0};
                                 ROWS_LOOP(j, i) {
                                     double acc = 0.0;
-                                    const int rl = S.row_len[i];
-                                    for (int q = 0; q < rl; ++q) {
-                                        const uint32_t e = S.row_ent[(size_t)q * mu + i];
-                                        acc = fma(sA[e & 0xFFFFu], sRHS[e >> 16], acc);
-                                    }
+                                    ROW_ENTRIES(i, e) acc = fma(sA[e & 0xFFFFu], sRHS[e >> 16], acc);
                                     if (uns) acc *= 1.0 / B.Eg[bmu + i];
                                     if ((hi[j] < kInfty * kMinScaling && acc > edi * nrm[0]) ||
                                         (lo[j] > -kInfty * kMinScaling && acc < -edi * nrm[0]))
-                                        viol = 1;
+                                        viol[0] = 1.0;
                                 }
-                                dic = !__syncthreads_or(viol);
+                                owners_max<1>(viol, sRed, oid);
+                                dic = viol[0] == 0.0;
                             }
                         }
                     }
@@ -847,10 +1109,13 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
                     }
                 }
                 if (!done && last) status = -2;
+                PHASE_MARK(PH_INFO);
             }
         }
 #undef RHO_OF
 #undef RINV_OF
+        if (oid == 0) *sCtrl = CTRL_EXIT;
+        __syncthreads(); // (E) releases the solver warps from this QP
 
         // ------------------------------------------------------------------ store
         const bool infeasible = status == -3 || status == 3 || status == -4 || status == 4 || status == -7;
@@ -867,10 +1132,9 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
             B.z_state[bmu + i] = infeasible ? 0.0 : z[j];
             B.y_state[bmu + i] = infeasible ? 0.0 : y[j];
         }
-        for (int e = tid; e < S.n_empty; e += NT) yo[S.empty_rows[e]] = infeasible ? qnan : 0.0;
-        if (tid == 0) {
+        for (int e = oid; e < S.n_empty; e += kOwners) yo[S.empty_rows[e]] = infeasible ? qnan : 0.0;
+        if (oid == 0) {
             B.rho_state[b] = rho;
-            B.flags[b] = 0;
             B.status[b] = status;
             B.iters[b] = iters_done;
             B.rho_updates[b] = rho_updates;
@@ -878,17 +1142,40 @@ __global__ void __launch_bounds__(NT, 2) gomp_admm_kernel(const DevSym S, const 
             B.dua_res[b] = dua_res;
         }
         fence_proxy_async(); // generic-proxy accesses to sA are ordered before the next QP's bulk copy
-        __syncthreads();
+        PHASE_MARK(PH_STORE);
     }
 }
 
+#undef sA
+#undef sP
+#undef sW
+#undef sRHS
+#undef sDinv
+#undef sOff
+#undef sRed
+#undef sRowEnt
+#undef sColRange
+#undef sPfEnt
+#undef sPuIJ
+#undef sRowPtr
+#undef sCscRow
+#undef sPfPtr
+#undef sOffTslot
+#undef sOffCol
+#undef sOffTrow
+#undef sBar
+#undef sWork
+#undef sCtrl
 #undef ROWS_LOOP
 #undef COLS_LOOP
+#undef ROW_ENTRIES
+#undef COL_ENTRIES
+#undef PF_ENTRIES
 
 // ---- launch interface (one explicit instantiation per translation unit) ------------------------------
 template <int RPT, int CPT, int BS>
 cudaError_t prepare_variant(size_t smem_bytes, int *ctas_per_sm) {
-    auto fn = gomp_admm_kernel<kThreads, RPT, CPT, BS>;
+    auto fn = gomp_admm_kernel<RPT, CPT, BS>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -897,7 +1184,7 @@ cudaError_t prepare_variant(size_t smem_bytes, int *ctas_per_sm) {
 template <int RPT, int CPT, int BS>
 cudaError_t launch_variant(const DevSym &S, const DevBatch &B, const DevSettings &st, int grid, size_t smem_bytes,
                            cudaStream_t stream) {
-    gomp_admm_kernel<kThreads, RPT, CPT, BS><<<grid, kThreads, smem_bytes, stream>>>(S, B, st);
+    gomp_admm_kernel<RPT, CPT, BS><<<grid, kThreads, smem_bytes, stream>>>(S, B, st);
     return cudaGetLastError();
 }
 

@@ -54,6 +54,13 @@ struct Symbolic {
     std::vector<uint32_t> col_start; // [n_pad]
     std::vector<uint8_t> col_len;    // [n_pad]
     std::vector<uint16_t> col_row;   // [colw * n_pad]
+    // compact views staged into shared memory by the kernel
+    std::vector<uint16_t> row_ptr;   // [m_used + 1] CSR pointers over compact rows
+    std::vector<uint32_t> row_csr;   // [nnzA] (pos << 16 | k), row-major
+    std::vector<uint16_t> csc_row;   // [nnzA] compact row of CSC entry k
+    std::vector<uint32_t> col_range; // [n_pad] (start << 8 | len) of position p in the CSC value array
+    std::vector<uint16_t> pf_ptr;    // [n_pad + 1] CSR pointers of the full-symmetric view of P
+    std::vector<uint32_t> pf_csr;    // (other_pos << 16 | kPu)
 
     // P, upper triangle in CSC order of the input
     std::vector<double> Pu_val;   // [nnzPu] raw values
@@ -257,6 +264,14 @@ inline bool analyse(Symbolic &sym, int64_t n, int64_t m, const int64_t *Pp, cons
             sym.row_len[(size_t)i] = (uint8_t)ent[(size_t)i].size();
             for (size_t j = 0; j < ent[(size_t)i].size(); ++j) sym.row_ent[j * sym.m_used + i] = ent[(size_t)i][j];
         }
+        sym.row_ptr.assign((size_t)sym.m_used + 1, 0);
+        sym.row_csr.clear();
+        for (int i = 0; i < sym.m_used; ++i) {
+            for (uint32_t e : ent[(size_t)i]) sym.row_csr.push_back(e);
+            sym.row_ptr[(size_t)i + 1] = (uint16_t)sym.row_csr.size();
+        }
+        sym.csc_row.assign((size_t)sym.nnzA, 0);
+        for (int64_t k = 0; k < sym.nnzA; ++k) sym.csc_row[(size_t)k] = (uint16_t)sym.row_compact[(size_t)Ai[k]];
         sym.col_start.assign((size_t)sym.n_pad, 0);
         sym.col_len.assign((size_t)sym.n_pad, 0);
         for (int64_t j = 0; j < n; ++j) {
@@ -265,6 +280,9 @@ inline bool analyse(Symbolic &sym, int64_t n, int64_t m, const int64_t *Pp, cons
             sym.colw = std::max(sym.colw, (int)len);
         }
         sym.col_row.assign((size_t)std::max(1, sym.colw) * sym.n_pad, 0);
+        sym.col_range.assign((size_t)sym.n_pad, 0);
+        for (int64_t j = 0; j < n; ++j)
+            sym.col_range[(size_t)sym.var_pos[(size_t)j]] = ((uint32_t)Ap[j] << 8) | (uint32_t)(Ap[j + 1] - Ap[j]);
         for (int64_t j = 0; j < n; ++j) {
             int p = sym.var_pos[(size_t)j];
             sym.col_start[(size_t)p] = (uint32_t)Ap[j];
@@ -290,6 +308,12 @@ inline bool analyse(Symbolic &sym, int64_t n, int64_t m, const int64_t *Pp, cons
         if (sym.pfw > 255) return sym.error = "a column of P has more than 255 entries", false;
         sym.pf_ent.assign((size_t)std::max(1, sym.pfw) * sym.n_pad, 0xFFFFFFFFu);
         sym.pf_len.assign((size_t)sym.n_pad, 0);
+        sym.pf_ptr.assign((size_t)sym.n_pad + 1, 0);
+        sym.pf_csr.clear();
+        for (int p = 0; p < sym.n_pad; ++p) {
+            for (uint32_t e : full[(size_t)p]) sym.pf_csr.push_back(e);
+            sym.pf_ptr[(size_t)p + 1] = (uint16_t)sym.pf_csr.size();
+        }
         for (int p = 0; p < sym.n_pad; ++p) {
             sym.pf_len[(size_t)p] = (uint8_t)full[(size_t)p].size();
             for (size_t j = 0; j < full[(size_t)p].size(); ++j) sym.pf_ent[j * sym.n_pad + p] = full[(size_t)p][j];

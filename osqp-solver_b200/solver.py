@@ -19,7 +19,7 @@ EXIT_NAMES = ["kOptimal", "kPrimalInfeasible", "kDualInfeasible", "kOptimalInacc
 
 EXPORTS = ["gomp_settings_default", "gomp_batch_create", "gomp_batch_setup", "gomp_batch_warm_start_x", "gomp_batch_solve",
            "gomp_batch_update", "gomp_batch_get", "gomp_batch_get_info", "gomp_batch_info", "gomp_batch_sync",
-           "gomp_batch_destroy", "gomp_last_error_string", "gomp_device_count", "gomp_version"]
+           "gomp_batch_destroy", "gomp_measure_peaks", "gomp_last_error_string", "gomp_device_count", "gomp_version"]
 
 
 class Settings(C.Structure):
@@ -45,6 +45,7 @@ class Info(C.Structure):
         ("flops_per_factor", C.c_int64), ("smem_bytes_per_factor", C.c_int64),
         ("flops_per_scaling", C.c_int64), ("smem_bytes_per_scaling", C.c_int64),
         ("flops_per_check", C.c_int64), ("smem_bytes_per_check", C.c_int64),
+        ("phase_cycles", C.c_double * 8), ("assemble_cycles", C.c_double),
     ]
 
 
@@ -201,7 +202,16 @@ class BatchQPSolver:
     def info(self):
         inf = Info()
         _check(lib().gomp_batch_info(self.h, C.byref(inf)))
-        return {k: getattr(inf, k) for k, _ in Info._fields_}
+        out = {k: getattr(inf, k) for k, _ in Info._fields_}
+        out["phase_cycles"] = list(inf.phase_cycles)
+        return out
+
+
+def measure_peaks():
+    """(fp64 TFLOP/s, shared-memory GB/s) measured on the current device."""
+    f, s = C.c_double(), C.c_double()
+    _check(lib().gomp_measure_peaks(C.byref(f), C.byref(s)))
+    return f.value, s.value
 
 
 def device_count():

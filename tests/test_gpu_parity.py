@@ -52,15 +52,15 @@ def oracle_batch(O, pat, d, settings=None):
 
 
 def test_gomp_batch_default_settings(env):
-    """BASELINE configs[1] shape (7-DoF, H=50), 96 problems incl. multi-check and infeasible ones."""
+    """BASELINE configs[1] shape (7-DoF, H=50), 320 problems incl. multi-check and infeasible ones."""
     pkg, O, pat = env
-    d = pkg.problem.generate(pat, 0, 96)
+    d = pkg.problem.generate(pat, 0, 320)
     s = make_solver(pkg, pat, d)
     s.set_warm_start(d["x0"])
     got = s.solve(want_y=True)
     ref = oracle_batch(O, pat, d)
     compare(got, ref)
-    assert (ref["exit_code"] != 0).any() and (ref["iters"] > 25).any()  # the sample exercises those paths
+    assert (ref["exit_code"] != 0).any() and (ref["iters"] > 25).any() and (ref["rho_updates"] > 0).any()  # paths exercised
     info = s.info()
     assert info["m_used"] == 1558 and info["block_size"] == 14 and info["num_blocks"] == 50
     s.close()
