@@ -94,7 +94,8 @@ def workload(pkg):
                         "1 gripper ball + 1 horizontal-line obstacle; cold setup + warm start + solve, OSQP default settings "
                         "(eps 1e-3, adaptive_rho_interval pinned to 25)",
             "n_dim": 7, "waypoints": 50, "n": pat.n, "m": pat.m, "nnzA": pat.nnzA, "batch_per_gpu": BATCH_PER_GPU,
-            "l2_policy": "inputs larger than L2 (305 MB of A_val/l/u per step vs 126 MB L2)"}
+            "l2_policy": "inputs larger than L2 (305 MB of A_val/l/u per step vs 126 MB L2)",
+            "batches_in_flight": 2}
     return cfg, pat, desc
 
 
@@ -154,24 +155,30 @@ def run_gpu(args):
             dict(A_val=(B, pat.nnzA), l=(B, pat.m), u=(B, pat.m), x0=(B, pat.n), start_goal=(B, 2 * cfg.n_dim)).items()}
     pkg.problem.generate(pat, first_id, B, out={k: v.numpy() for k, v in host.items()})
     dev = {k: host[k].cuda() for k in ("A_val", "l", "u", "x0")}
-    stream = torch.cuda.Stream()  # the library launches on this stream; events below are recorded on it
-    torch.cuda.set_stream(stream)
+    # Two batches in flight: consecutive steps alternate between two handles on two streams, so the few
+    # QPs of a batch that need thousands of ADMM iterations (max_iter = 4000) overlap with the next batch
+    # instead of leaving 146 SMs idle.  Every step still is a full cold setup + warm start + solve.
+    PIPE = 2
+    streams = [torch.cuda.Stream() for _ in range(PIPE)]
+    main = torch.cuda.current_stream()
 
-    def make(borrow):
+    def make(borrow, stream):
         st = S.default_settings(borrow_inputs=1 if borrow else 0, stream=stream.cuda_stream, device=local_rank)
         return S.BatchQPSolver(pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx,
                                batch=B, settings=st, var_order=pat.var_order, block_size=pat.block_size)
 
-    solver = make(True)
+    solvers = [make(True, streams[k]) for k in range(PIPE)]
+    solver = solvers[0]
     x_dev = torch.empty((B, pat.n), dtype=torch.float64, device="cuda")
     code = np.empty(B, dtype=np.int32)
     iters = np.empty(B, dtype=np.int32)
     rup = np.empty(B, dtype=np.int32)
 
-    def step_resident():
-        solver.setup(dev["A_val"], dev["l"], dev["u"])
-        solver.set_warm_start(dev["x0"])
-        solver.solve_async()
+    def step_resident(k=0):
+        sv = solvers[k % PIPE]
+        sv.setup(dev["A_val"], dev["l"], dev["u"])
+        sv.set_warm_start(dev["x0"])
+        sv.solve_async()
 
     def barrier():
         if world > 1:
@@ -183,35 +190,46 @@ def run_gpu(args):
     def gather_results():
         # problems are independent: the only collective is the final gather of the solutions (NCCL)
         if world > 1:
-            solver.get(x=x_dev, exit_code=code, iters=iters, rho_updates=rup)
+            solvers[-1].get(x=x_dev, exit_code=code, iters=iters, rho_updates=rup)
             dist.gather(x_dev, gathered, dst=0)
 
-    for _ in range(args.warmup):
-        step_resident()
-        gather_results()
+    def run_steps(nsteps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(main)
+        for st_ in streams:
+            st_.wait_event(ev0)
+        for k in range(nsteps):
+            step_resident(k)
+        for st_ in streams:
+            e = torch.cuda.Event()
+            e.record(st_)
+            main.wait_event(e)
+        ev1.record(main)
+        return ev0, ev1
+
+    run_steps(args.warmup)
     barrier()
-    launches0 = solver.info()["kernel_launches"]
+    gather_results()
+    barrier()
+    launches0 = sum(sv.info()["kernel_launches"] for sv in solvers)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
     barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step_resident()
-        gather_results()
-        if world == 1:
-            pass
-    ev1.record(stream)
+    ev0, ev1 = run_steps(args.steps)
+    gather_results()  # N > 1: the NCCL gather of the last batch's solutions, inside the timed region
+    if world > 1:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record(main)
     barrier()
     clocks = sampler.stop()
     total_ms = ev0.elapsed_time(ev1)
     r = solver.get(x=x_dev, exit_code=code, iters=iters, rho_updates=rup)
     info = solver.info()
-    launches = info["kernel_launches"] - launches0
-    # per-launch duration of the dominant (only) kernel, CUDA events on its stream, live
+    launches = sum(sv.info()["kernel_launches"] for sv in solvers) - launches0
+    # per-launch duration of the dominant (only) kernel, CUDA events on its stream, live, one batch alone
     for _ in range(3):
-        step_resident()
+        step_resident(0)
         solver.sync()
         kernel_ms.append(solver.info()["last_solve_ms"])
     kernel_avg_ms = float(np.mean(kernel_ms))
@@ -223,7 +241,9 @@ def run_gpu(args):
     value = world * B * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers (copies inside the timed region)
-    solver_e2e = make(False)
+    stream = streams[0]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    solver_e2e = make(False, stream)
     x_host = torch.empty((B, pat.n), dtype=torch.float64).pin_memory()
 
     def step_e2e():

@@ -172,14 +172,14 @@ struct gomp_batch {
     const double *x0_src = nullptr;
     // pattern arrays on the device
     DevArray<int32_t> d_pos_var, d_used_rows, d_empty_rows;
-    DevArray<uint32_t> d_row_csr, d_col_range, d_pf_csr, d_Pu_ij, d_sd_ptr, d_so_ptr;
+    DevArray<uint32_t> d_row_csr, d_row_range, d_col_range, d_pf_csr, d_Pu_ij, d_sd_ptr, d_so_ptr;
     DevArray<uint16_t> d_row_ptr, d_csc_row, d_pf_ptr, d_offT_slot, d_sd_pk, d_so_pk, d_tri_rc;
     DevArray<uint8_t> d_sd_kind;
     DevArray<int8_t> d_off_col, d_offT_row;
     DevArray<double> d_Pu_val;
     DevArray<gomp::Contrib> d_sd_con, d_so_con;
     // per-batch storage
-    DevArray<double> d_A, d_l, d_u, d_q, d_x0, d_xs, d_zs, d_ys, d_rho, d_E, d_D, d_qs, d_dy, d_dx, d_xo, d_yo, d_pri, d_dua, d_obj;
+    DevArray<double> d_A, d_l, d_u, d_q, d_x0, d_xs, d_zs, d_ys, d_rho, d_E, d_D, d_qs, d_dy, d_dx, d_Lg, d_Ug, d_xo, d_yo, d_pri, d_dua, d_obj;
     DevArray<unsigned long long> d_prof;
     DevArray<int> d_status, d_iters, d_rup, d_counter;
     const double *A_src = nullptr, *l_src = nullptr, *u_src = nullptr, *q_src = nullptr; // borrowed device inputs
@@ -197,6 +197,7 @@ int upload_pattern(gomp_batch *h) {
     UP(d_empty_rows, empty_rows);
     UP(d_row_csr, row_csr);
     UP(d_row_ptr, row_ptr);
+    UP(d_row_range, row_range);
     UP(d_csc_row, csc_row);
     UP(d_col_range, col_range);
     UP(d_pf_csr, pf_csr);
@@ -226,8 +227,16 @@ int upload_pattern(gomp_batch *h) {
     d.n = (int)s.n; d.m = (int)s.m; d.nnzA = (int)s.nnzA; d.nnzPu = (int)s.nnzPu; d.m_used = s.m_used; d.bs = s.bs;
     d.T = s.T; d.n_pad = s.n_pad; d.ow = s.ow; d.owT = s.owT;
     d.n_empty = (int)s.empty_rows.size(); d.noff = std::max(0, s.T - 1) * s.bs * s.ow; d.npf = (int)s.pf_csr.size();
+    d.uniform_off = s.T >= 2 ? 1 : 0;
+    for (int t = 1; t + 1 < s.T && d.uniform_off; ++t) {
+        for (int e = 0; e < s.bs * s.ow; ++e)
+            if (s.off_col[(size_t)t * s.bs * s.ow + e] != s.off_col[e]) d.uniform_off = 0;
+        for (int e = 0; e < s.bs * s.owT; ++e)
+            if (s.offT_row[(size_t)t * s.bs * s.owT + e] != s.offT_row[e] || s.offT_slot[(size_t)t * s.bs * s.owT + e] != s.offT_slot[e])
+                d.uniform_off = 0;
+    }
     d.pos_var = h->d_pos_var.p; d.used_rows = h->d_used_rows.p; d.empty_rows = h->d_empty_rows.p;
-    d.row_csr = h->d_row_csr.p; d.col_range = h->d_col_range.p; d.pf_csr = h->d_pf_csr.p; d.Pu_ij = h->d_Pu_ij.p;
+    d.row_csr = h->d_row_csr.p; d.row_range = h->d_row_range.p; d.col_range = h->d_col_range.p; d.pf_csr = h->d_pf_csr.p; d.Pu_ij = h->d_Pu_ij.p;
     d.row_ptr = h->d_row_ptr.p; d.csc_row = h->d_csc_row.p; d.pf_ptr = h->d_pf_ptr.p; d.offT_slot = h->d_offT_slot.p;
     d.off_col = h->d_off_col.p; d.offT_row = h->d_offT_row.p; d.Pu_val = h->d_Pu_val.p;
     d.sd_ptr = h->d_sd_ptr.p; d.sd_con = h->d_sd_con.p; d.sd_pk = h->d_sd_pk.p; d.sd_kind = h->d_sd_kind.p;
@@ -246,19 +255,41 @@ int upload_pattern(gomp_batch *h) {
     d.oRHS = take(8 * (size_t)d.n_pad);
     d.oDinv = take(8 * (size_t)d.T * bb);
     d.oOff = take(8 * (size_t)std::max(1, d.noff));
-    d.oV = take(8 * 64);
+    d.oV = take(8 * 512); // per-warp broadcast lines (256 bytes apart, double-buffered)
     d.oScr = take(8 * std::max<size_t>(2 * bb, 256)); // per-warp scratch (generic path) / pivot row+column exchange of the factor groups
     d.oRed = take(8 * (size_t)kRedK * (kThreads / 32));
-    d.oRowEnt = take(4 * (size_t)d.nnzA);
+    d.oRowRange = take(4 * (size_t)std::max(1, d.m_used));
+    d.oRowEnt = take(4 * ((size_t)d.nnzA + 4));
     d.oColRange = take(4 * (size_t)d.n_pad);
-    d.oPfEnt = take(4 * (size_t)std::max(1, d.npf));
-    d.oPuIJ = take(4 * (size_t)std::max(1, d.nnzPu));
-    d.oRowPtr = take(2 * ((size_t)d.m_used + 1));
-    d.oCscRow = take(2 * (size_t)d.nnzA);
-    d.oPfPtr = take(2 * ((size_t)d.n_pad + 1));
+    d.oCscRow = take(2 * ((size_t)d.nnzA + 4));
     d.oOffTslot = take(2 * std::max<size_t>(1, noffT));
     d.oOffCol = take(std::max<size_t>(1, (size_t)d.noff));
     d.oOffTrow = take(std::max<size_t>(1, noffT));
+    d.oRowPtr = 0;
+    // optional residents, in order of benefit, as long as everything still fits in 227 KB per CTA:
+    // the scaled bounds l, u (read every iteration) and the P-side pattern arrays (scaling / residuals only)
+    const size_t kSmemMax = (size_t)227 * 1024;
+    {
+        const size_t before = o;
+        d.oLo = take(8 * (size_t)std::max(1, d.m_used));
+        d.oHi = take(8 * (size_t)std::max(1, d.m_used));
+        d.bounds_in_smem = 1;
+        if (o + 16 > kSmemMax) {
+            o = before;
+            d.bounds_in_smem = 0;
+        }
+    }
+    {
+        const size_t before = o;
+        d.oPfEnt = take(4 * (size_t)std::max(1, d.npf));
+        d.oPuIJ = take(4 * (size_t)std::max(1, d.nnzPu));
+        d.oPfPtr = take(2 * ((size_t)d.n_pad + 1));
+        d.p_in_smem = 1;
+        if (o + 16 > kSmemMax) {
+            o = before;
+            d.p_in_smem = 0;
+        }
+    }
     d.oBar = take(16);
     h->smem_bytes = o;
     return GOMP_OK;
@@ -405,13 +436,13 @@ int gomp_batch_destroy(gomp_batch *h) {
     if (!h) return GOMP_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    h->d_pos_var.release(); h->d_used_rows.release(); h->d_empty_rows.release(); h->d_row_csr.release(); h->d_col_range.release();
+    h->d_pos_var.release(); h->d_used_rows.release(); h->d_empty_rows.release(); h->d_row_csr.release(); h->d_row_range.release(); h->d_col_range.release();
     h->d_pf_csr.release(); h->d_Pu_ij.release(); h->d_sd_ptr.release(); h->d_so_ptr.release(); h->d_row_ptr.release();
     h->d_csc_row.release(); h->d_pf_ptr.release(); h->d_offT_slot.release(); h->d_sd_pk.release(); h->d_so_pk.release();
     h->d_sd_kind.release(); h->d_off_col.release(); h->d_offT_row.release(); h->d_Pu_val.release(); h->d_sd_con.release();
     h->d_so_con.release();
     h->d_A.release(); h->d_l.release(); h->d_u.release(); h->d_q.release(); h->d_x0.release(); h->d_xs.release();
-    h->d_zs.release(); h->d_ys.release(); h->d_rho.release(); h->d_E.release(); h->d_D.release(); h->d_qs.release(); h->d_dx.release(); h->d_tri_rc.release(); h->d_dy.release(); h->d_xo.release();
+    h->d_zs.release(); h->d_ys.release(); h->d_rho.release(); h->d_E.release(); h->d_D.release(); h->d_qs.release(); h->d_dx.release(); h->d_Lg.release(); h->d_Ug.release(); h->d_tri_rc.release(); h->d_dy.release(); h->d_xo.release();
     h->d_yo.release(); h->d_pri.release(); h->d_dua.release(); h->d_obj.release();
     h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -502,6 +533,10 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     ALLOC(d_E, B * mu);
     ALLOC(d_D, B * np);
     ALLOC(d_dx, B * np);
+    if (!h->ds.bounds_in_smem) {
+        ALLOC(d_Lg, B * mu);
+        ALLOC(d_Ug, B * mu);
+    }
     ALLOC(d_dy, B * mu);
     ALLOC(d_xo, B * (size_t)n);
     ALLOC(d_yo, B * (size_t)std::max<int64_t>(m, 1));
@@ -572,7 +607,7 @@ int gomp_batch_solve(gomp_batch *h) {
     b.A_pitch = s.nnzA;
     b.bulk_ok = (s.nnzA % 2 == 0) && (((uintptr_t)h->A_src) % 16 == 0) && s.nnzA > 0 && (size_t)s.nnzA * 8 < (1u << 20);
     b.x_state = h->d_xs.p; b.z_state = h->d_zs.p; b.y_state = h->d_ys.p; b.rho_state = h->d_rho.p; b.flag_bits = h->pending_flags;
-    b.Eg = h->d_E.p; b.Dg = h->d_D.p; b.qs = h->d_qs.p; b.dyg = h->d_dy.p; b.dxg = h->d_dx.p; b.x_out = h->d_xo.p; b.y_out = h->d_yo.p;
+    b.Eg = h->d_E.p; b.Dg = h->d_D.p; b.qs = h->d_qs.p; b.dyg = h->d_dy.p; b.dxg = h->d_dx.p; b.Lg = h->d_Lg.p; b.Ug = h->d_Ug.p; b.x_out = h->d_xo.p; b.y_out = h->d_yo.p;
     b.status = h->d_status.p; b.iters = h->d_iters.p; b.rho_updates = h->d_rup.p;
     b.pri_res = h->d_pri.p; b.dua_res = h->d_dua.p; b.obj_val = h->d_obj.p; b.work_counter = h->d_counter.p; b.prof = h->d_prof.p;
     CUDA_TRY(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));

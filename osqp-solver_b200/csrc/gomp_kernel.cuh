@@ -46,9 +46,12 @@ constexpr int kRedK = 14;                  // widest multi-value block reduction
 // ---- device-side views ------------------------------------------------------------------------
 struct DevSym {
     int n, m, nnzA, nnzPu, m_used, bs, T, n_pad, ow, owT, n_empty, noff, npf;
+    int uniform_off; // every off-diagonal block has the same sparsity pattern
+    int bounds_in_smem; // scaled l, u of the QP fit in shared memory (else: per-QP global scratch)
+    int p_in_smem; // the P-side pattern arrays (pf_csr, pf_ptr, Pu_ij) fit in shared memory
     const int32_t *pos_var, *used_rows, *empty_rows;
     // pattern arrays (global copies; staged into shared memory once per kernel)
-    const uint32_t *row_csr, *col_range, *pf_csr, *Pu_ij;
+    const uint32_t *row_csr, *row_range, *col_range, *pf_csr, *Pu_ij;
     const uint16_t *row_ptr, *csc_row, *pf_ptr, *offT_slot;
     const int8_t *off_col, *offT_row;
     const double *Pu_val;
@@ -62,7 +65,7 @@ struct DevSym {
     const uint16_t *so_pk;
     const uint16_t *tri_rc; // packed lower index -> (row << 8 | col)
     // shared-memory carve-up (byte offsets)
-    int oA, oP, oW, oRHS, oDinv, oOff, oV, oScr, oRed, oRowEnt, oColRange, oPfEnt, oPuIJ, oRowPtr, oCscRow, oPfPtr, oOffTslot,
+    int oA, oP, oW, oRHS, oLo, oHi, oDinv, oOff, oV, oScr, oRed, oRowRange, oRowEnt, oColRange, oPfEnt, oPuIJ, oRowPtr, oCscRow, oPfPtr, oOffTslot,
         oOffCol, oOffTrow, oBar;
 };
 
@@ -73,7 +76,7 @@ struct DevBatch {
     long long A_pitch;
     double *x_state, *z_state, *y_state, *rho_state;
     int flag_bits; // bit0: cold start, bit1: primal warm start pending (whole batch)
-    double *Eg, *Dg, *qs, *dyg, *dxg;
+    double *Eg, *Dg, *qs, *dyg, *dxg, *Lg, *Ug;
     double *x_out, *y_out;
     int *status, *iters, *rho_updates;
     double *pri_res, *dua_res, *obj_val;
@@ -227,164 +230,83 @@ __device__ __forceinline__ double apply_dinv(const SolverCtx &C, int t, double y
     return u;
 }
 
-// Pivot block of stage t: D_t = S_tt - (neighbour update), inverted in place in shared memory.
-//   mode bit 1: minus Off_{t-1} Dinv_{t-1} Off_{t-1}';  mode bit 2: minus Off_t' Dinv_{t+1} Off_t
-//   (both at the middle stage).
-// One warp; all 32 lanes sweep the bs*bs entries.  Deliberately compact (runtime loops, not inlined):
-// a fully unrolled register version stalls on instruction fetch -- one warp cannot hide I-cache misses.
-template <int BS>
-static __device__ __noinline__ void factor_block(const SolverCtx &C, int t, int mode, int lane) {
-    const int bs = BS > 0 ? BS : C.bs;
-    const int nn = bs * bs;
-    double *M = C.dinv() + (size_t)t * nn;
-#pragma unroll 1
-    for (int pass = 1; pass <= 2; ++pass) {
-        if (!(mode & pass)) continue;
-        const bool above = pass == 1;
-        const int tb = above ? t - 1 : t; // off-diagonal block involved
-        const double *Dn = C.dinv() + (size_t)(above ? t - 1 : t + 1) * nn;
-        const double *blk = C.off() + (size_t)tb * bs * C.ow;
-        const int cnt = above ? C.ow : C.owT;
-#pragma unroll 1
-        for (int e = lane; e < nn; e += 32) {
-            const int r = e / bs, c = e - r * bs;
-            double acc = 0.0;
-            for (int s = 0; s < cnt; ++s) {
-                int a;
-                double va = 0.0;
-                if (above) {
-                    a = C.offCol()[(tb * bs + r) * C.ow + s];
-                    if (a >= 0) va = blk[r * C.ow + s];
-                } else {
-                    a = C.offTrow()[(tb * bs + r) * C.owT + s];
-                    if (a >= 0) va = blk[C.offTslot()[(tb * bs + r) * C.owT + s]];
-                }
-                if (a < 0) continue;
-                for (int s2 = 0; s2 < cnt; ++s2) {
-                    int b2;
-                    double vb = 0.0;
-                    if (above) {
-                        b2 = C.offCol()[(tb * bs + c) * C.ow + s2];
-                        if (b2 >= 0) vb = blk[c * C.ow + s2];
-                    } else {
-                        b2 = C.offTrow()[(tb * bs + c) * C.owT + s2];
-                        if (b2 >= 0) vb = blk[C.offTslot()[(tb * bs + c) * C.owT + s2]];
-                    }
-                    if (b2 >= 0) acc += va * Dn[a * bs + b2] * vb;
-                }
-            }
-            M[e] -= acc;
-        }
-        __syncwarp();
-    }
-    // Gauss-Jordan without pivoting (SPD block).  The reciprocal of the next pivot is started as soon as
-    // the trailing update of step k is visible, so the division overlaps the row/column fix-up of step k.
-    double pinv = 1.0 / M[0];
-#pragma unroll 1
-    for (int k = 0; k < bs; ++k) {
-        const double *rowk = M + k * bs;
-#pragma unroll 1
-        for (int e = lane; e < nn; e += 32) {
-            const int i = e / bs, j = e - i * bs;
-            if (i != k && j != k) M[e] = fma(-(M[i * bs + k] * pinv), rowk[j], M[e]);
-        }
-        __syncwarp();
-        const double pnext = k + 1 < bs ? 1.0 / M[(k + 1) * bs + k + 1] : 0.0;
-        if (lane < bs) {
-            if (lane != k) {
-                M[lane * bs + k] = -(M[lane * bs + k] * pinv);
-                M[k * bs + lane] *= pinv;
-            } else {
-                M[k * bs + k] = pinv;
-            }
-        }
-        pinv = pnext;
-        __syncwarp();
-    }
-}
-
-// ---- software-pipelined substitution step (fast path: compile-time block size, <= 2 off-diagonal
-// entries per block row/column).  Everything that does not depend on the previous stage's result --
-// the lane's row of the inverted pivot block, its right-hand side entry, the off-diagonal values and
-// indices -- is fetched into registers one step ahead; the dependent part is: two gathers from the
-// previous stage, two FMAs, one shared-memory broadcast of the block vector, 2N FMAs.
-template <int BS>
-struct StepRegs {
-    double m[BS > 0 ? BS : 2];
-    double b, ov0, ov1;
-    int oi0, oi1;
+// ---- substitution step of the fast path (compile-time block size, <= 2 off-diagonal entries per block
+// row / column).  The previous stage's result stays in a register of its lane and is gathered with two
+// shuffles; everything independent of it -- the lane's row of the inverted pivot block, its right-hand
+// side entry, the off-diagonal values -- is loaded first.  The block vector is broadcast through a
+// double-buffered shared-memory line, so one __syncwarp per step.
+struct OffPattern { // per-lane indices of one off-diagonal block row (forward) and column (transposed)
+    int oi0, oi1;   // columns of Off_t[lane][.] (-1: none)
+    int ti0, ti1;   // rows r with Off_t[r][lane] != 0 (-1: none)
+    int ts0, ts1;   // their value slots inside block t
 };
+__device__ __forceinline__ void load_off_pattern(const SolverCtx &C, int tb, int rl, OffPattern &P) {
+    const int bf = (tb * C.bs + rl) * C.ow, bt = (tb * C.bs + rl) * C.owT;
+    P.oi0 = C.offCol()[bf];
+    P.oi1 = C.ow > 1 ? C.offCol()[bf + 1] : -1;
+    P.ti0 = C.offTrow()[bt];
+    P.ts0 = C.offTslot()[bt];
+    P.ti1 = C.owT > 1 ? C.offTrow()[bt + 1] : -1;
+    P.ts1 = C.owT > 1 ? C.offTslot()[bt + 1] : 0;
+}
+// fwd:  returns (Dinv_t (b - off . uprev))[lane]        bwd:  returns (b - Dinv_t (off . uprev))[lane]
 // tb < 0: no off-diagonal part.  transposed: use Off_tb' (columns of stage tb from stage tb+1).
 template <int BS>
-__device__ __forceinline__ void chain_prefetch(const SolverCtx &C, int t, int tb, bool transposed, int lane, StepRegs<BS> &P) {
+__device__ __forceinline__ double chain_step(const SolverCtx &C, int t, int tb, bool transposed, bool fwd, double uprev, int lane,
+                                             const OffPattern &P) {
     constexpr int NB = BS > 0 ? BS : 2;
     const int rl = lane < NB ? lane : NB - 1;
+    // ---- independent of the previous stage
     const double *row = C.dinv() + ((size_t)t * NB + rl) * NB;
+    double m[NB];
 #pragma unroll
     for (int c = 0; c < NB; c += 2) {
         const double2 d = *reinterpret_cast<const double2 *>(row + c);
-        P.m[c] = d.x;
-        P.m[c + 1] = d.y;
+        m[c] = d.x;
+        m[c + 1] = d.y;
     }
-    P.b = C.rhs()[t * NB + rl];
-    int a0 = -1, a1 = -1;
-    double v0 = 0.0, v1 = 0.0;
+    const double b = C.rhs()[t * NB + rl];
+    double ov0 = 0.0, ov1 = 0.0;
+    int s0 = 0, s1 = 0;
     if (tb >= 0) {
         if (!transposed) {
-            const int base = (tb * NB + rl) * C.ow;
-            a0 = C.offCol()[base];
-            v0 = C.off()[base];
-            if (C.ow > 1) {
-                a1 = C.offCol()[base + 1];
-                v1 = C.off()[base + 1];
-            }
+            const double *ob = C.off() + (size_t)(tb * NB + rl) * C.ow;
+            s0 = P.oi0;
+            s1 = P.oi1;
+            if (s0 >= 0) ov0 = ob[0];
+            if (s1 >= 0) ov1 = ob[1];
         } else {
-            const int base = (tb * NB + rl) * C.owT;
             const double *blk = C.off() + (size_t)tb * NB * C.ow;
-            a0 = C.offTrow()[base];
-            v0 = blk[C.offTslot()[base]];
-            if (C.owT > 1) {
-                a1 = C.offTrow()[base + 1];
-                v1 = blk[C.offTslot()[base + 1]];
-            }
+            s0 = P.ti0;
+            s1 = P.ti1;
+            if (s0 >= 0) ov0 = blk[P.ts0];
+            if (s1 >= 0) ov1 = blk[P.ts1];
         }
     }
-    P.oi0 = a0 >= 0 ? a0 : 0;
-    P.ov0 = a0 >= 0 ? v0 : 0.0;
-    P.oi1 = a1 >= 0 ? a1 : 0;
-    P.ov1 = a1 >= 0 ? v1 : 0.0;
-}
-// fwd:  rhs_t <- Dinv_t (b - off . src)        bwd:  rhs_t <- b - Dinv_t (off . src)
-template <int BS>
-__device__ __forceinline__ void chain_apply(const SolverCtx &C, int t, int src_stage, bool fwd, int lane, const StepRegs<BS> &P) {
-    constexpr int NB = BS > 0 ? BS : 2;
-    const double *src = C.rhs() + src_stage * NB;
-    const double off = fma(P.ov0, src[P.oi0], P.ov1 * src[P.oi1]);
-    const double v = fwd ? P.b - off : off;
-    if (lane < NB) C.vbuf()[lane] = v;
+    // ---- dependent part
+    const double up0 = __shfl_sync(0xffffffffu, uprev, s0 >= 0 ? s0 : 0);
+    const double up1 = __shfl_sync(0xffffffffu, uprev, s1 >= 0 ? s1 : 0);
+    const double off = fma(ov0, up0, ov1 * up1);
+    const double v = fwd ? b - off : off;
+    double *vb = C.vbuf() + (t & 1) * 16;
+    if (lane < NB) vb[lane] = v;
     __syncwarp();
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
     for (int c = 0; c < NB; c += 2) {
-        const double2 w = *reinterpret_cast<const double2 *>(C.vbuf() + c);
+        const double2 w = *reinterpret_cast<const double2 *>(vb + c);
         if ((c >> 1) & 1) {
-            a2 = fma(P.m[c], w.x, a2);
-            a3 = fma(P.m[c + 1], w.y, a3);
+            a2 = fma(m[c], w.x, a2);
+            a3 = fma(m[c + 1], w.y, a3);
         } else {
-            a0 = fma(P.m[c], w.x, a0);
-            a1 = fma(P.m[c + 1], w.y, a1);
+            a0 = fma(m[c], w.x, a0);
+            a1 = fma(m[c + 1], w.y, a1);
         }
     }
     const double acc = (a0 + a1) + (a2 + a3);
-    if (lane < NB) C.rhs()[t * NB + lane] = fwd ? acc : P.b - acc;
-    __syncwarp();
-}
-
-template <int BS>
-__device__ __forceinline__ void chain_step(const SolverCtx &C, int t, int tb, bool transposed, int src_stage, bool fwd, int lane) {
-    StepRegs<BS> P;
-    chain_prefetch<BS>(C, t, tb, transposed, lane, P);
-    chain_apply<BS>(C, t, src_stage, fwd, lane, P);
+    const double res = fwd ? acc : b - acc;
+    if (lane < NB) C.rhs()[t * NB + lane] = res;
+    return res;
 }
 
 // ================================================================================================
@@ -405,7 +327,7 @@ enum { PH_LOAD = 0, PH_SCALE, PH_FACTOR, PH_RHS, PH_SOLVE, PH_UPDATE, PH_INFO, P
 #define COLS_LOOP(c, p) _Pragma("unroll") for (int c = 0, p = oid; c < CPT; ++c, p += kOwners) if (p < np)
 // for every entry e = (pos << 16 | k) of compact row i
 #define ROW_ENTRIES(i, e) \
-    for (int q__ = sRowPtr[i], q1__ = sRowPtr[(i) + 1]; q__ < q1__; ++q__) \
+    for (int q__ = (int)(sRowRange[i] >> 8), q1__ = q__ + (int)(sRowRange[i] & 0xFFu); q__ < q1__; ++q__) \
         if (const uint32_t e = sRowEnt[q__]; true)
 // for every CSC value index k of the variable at position p
 #define COL_ENTRIES(p, k) for (int k = (int)(sColRange[p] >> 8), k1__ = k + (int)(sColRange[p] & 0xFFu); k < k1__; ++k)
@@ -424,7 +346,7 @@ enum { PH_LOAD = 0, PH_SCALE, PH_FACTOR, PH_RHS, PH_SOLVE, PH_UPDATE, PH_INFO, P
 constexpr int kFactorGroup = 224; // threads per chain group (warps 0-6: top chain, warps 7-13: bottom chain)
 
 template <int BS>
-static __device__ __noinline__ void factor_block_group(const DevSym &S, unsigned char *smem_raw, int t, int mode, int g, int gl) {
+__device__ __forceinline__ void factor_block_group(const DevSym &S, unsigned char *smem_raw, int t, int mode, int g, int gl) {
     const int bs = BS > 0 ? BS : S.bs;
     const int nn = bs * bs;
     constexpr int EPL = BS > 0 ? (BS * BS + kFactorGroup - 1) / kFactorGroup : 5; // entries per thread (bs <= 32)
@@ -531,10 +453,47 @@ __device__ __forceinline__ void factor_cooperative(const DevSym &S, unsigned cha
     }
 }
 
+// ---- sparse dot products of the owners, 4 entries in flight ---------------------------------------------
+// row i of A times a dense vector in shared memory; `range` = (first entry << 8 | length), entries are
+// (position << 16 | value index).  The entry array is padded so that reading 3 entries past a row is legal;
+// the surplus products are never accumulated.
+__device__ __forceinline__ double row_dot4(const uint32_t *__restrict__ ent, uint32_t range, const double *__restrict__ A,
+                                           const double *__restrict__ vec) {
+    int q = (int)(range >> 8);
+    const int q1 = q + (int)(range & 0xFFu);
+    double acc = 0.0;
+    for (; q < q1; q += 4) {
+        const uint32_t e0 = ent[q], e1 = ent[q + 1], e2 = ent[q + 2], e3 = ent[q + 3];
+        const double a0 = A[e0 & 0xFFFFu], a1 = A[e1 & 0xFFFFu], a2 = A[e2 & 0xFFFFu], a3 = A[e3 & 0xFFFFu];
+        const double v0 = vec[e0 >> 16], v1 = vec[e1 >> 16], v2 = vec[e2 >> 16], v3 = vec[e3 >> 16];
+        acc = fma(a0, v0, acc);
+        if (q + 1 < q1) acc = fma(a1, v1, acc);
+        if (q + 2 < q1) acc = fma(a2, v2, acc);
+        if (q + 3 < q1) acc = fma(a3, v3, acc);
+    }
+    return acc;
+}
+// column of A (contiguous value range) times a row-indexed vector: sum_k A[k] * vec[rowOf[k]]
+__device__ __forceinline__ double col_dot4(uint32_t range, const double *__restrict__ A, const uint16_t *__restrict__ rowOf,
+                                           const double *__restrict__ vec, double acc) {
+    int k = (int)(range >> 8);
+    const int k1 = k + (int)(range & 0xFFu);
+    for (; k < k1; k += 4) {
+        const int r0 = rowOf[k], r1 = rowOf[k + 1], r2 = rowOf[k + 2], r3 = rowOf[k + 3];
+        const double a0 = A[k], a1 = A[k + 1], a2 = A[k + 2], a3 = A[k + 3];
+        const double v0 = vec[r0];
+        acc = fma(a0, v0, acc);
+        if (k + 1 < k1) acc = fma(a1, vec[r1], acc);
+        if (k + 2 < k1) acc = fma(a2, vec[r2], acc);
+        if (k + 3 < k1) acc = fma(a3, vec[r3], acc);
+    }
+    return acc;
+}
+
 // Assembly of S = P + sigma I + A' diag(rho) A into the full-row pivot blocks and the ELL
 // off-diagonal blocks; destination driven (deterministic, no atomics), every thread of the CTA helps.
 // sW holds rho per compact row.
-static __device__ __noinline__ void assemble_S(const DevSym &S, double sigma, const double *sW, const double *sA, const double *sP,
+__device__ __forceinline__ void assemble_S(const DevSym &S, double sigma, const double *sW, const double *sA, const double *sP,
                                                double *sDinv, double *sOff, int tid, int bs) {
     const int dpb = bs * (bs + 1) / 2, ndiag = S.T * dpb, bb = bs * bs;
     for (int e = tid; e < ndiag; e += kThreads) {
@@ -569,15 +528,7 @@ static __device__ __noinline__ void assemble_S(const DevSym &S, double sigma, co
 // control word the owners publish for the solver warps before every CTA-wide rendezvous
 enum { CTRL_SOLVE = 0, CTRL_FACTOR = 1, CTRL_EXIT = 2 };
 
-template <int RPT, int CPT, int BS>
-__global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, const DevBatch B, const DevSettings st) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool owner = tid >= kSolverThreads;
-    const int oid = tid - kSolverThreads;
-    const int bs = BS > 0 ? BS : S.bs;
-    const int T = S.T, np = S.n_pad, mu = S.m_used, h = S.T / 2, bb = bs * bs;
-    // shared-memory regions: addressed as base + constant-bank offset, no pointer registers kept alive
+// shared-memory regions: addressed as base + constant-bank offset, no pointer registers kept alive
 #define sA (reinterpret_cast<double *>(smem_raw + S.oA))
 #define sP (reinterpret_cast<double *>(smem_raw + S.oP))
 #define sW (reinterpret_cast<double *>(smem_raw + S.oW))
@@ -586,12 +537,9 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
 #define sOff (reinterpret_cast<double *>(smem_raw + S.oOff))
 #define sRed (reinterpret_cast<double *>(smem_raw + S.oRed))
 #define sRowEnt (reinterpret_cast<uint32_t *>(smem_raw + S.oRowEnt))
+#define sRowRange (reinterpret_cast<uint32_t *>(smem_raw + S.oRowRange))
 #define sColRange (reinterpret_cast<uint32_t *>(smem_raw + S.oColRange))
-#define sPfEnt (reinterpret_cast<uint32_t *>(smem_raw + S.oPfEnt))
-#define sPuIJ (reinterpret_cast<uint32_t *>(smem_raw + S.oPuIJ))
-#define sRowPtr (reinterpret_cast<uint16_t *>(smem_raw + S.oRowPtr))
 #define sCscRow (reinterpret_cast<uint16_t *>(smem_raw + S.oCscRow))
-#define sPfPtr (reinterpret_cast<uint16_t *>(smem_raw + S.oPfPtr))
 #define sOffTslot (reinterpret_cast<uint16_t *>(smem_raw + S.oOffTslot))
 #define sOffCol (reinterpret_cast<int8_t *>(smem_raw + S.oOffCol))
 #define sOffTrow (reinterpret_cast<int8_t *>(smem_raw + S.oOffTrow))
@@ -599,16 +547,155 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
 #define sWork (reinterpret_cast<int *>(smem_raw + S.oBar + 8))
 #define sCtrl (reinterpret_cast<volatile int *>(smem_raw + S.oBar + 12))
 
+// ================================================================================================
+//                       solver role (warps 0 and 1): one QP's linear algebra
+// ================================================================================================
+template <int BS>
+static __device__ __noinline__ void solver_role(const DevSym &S, double sigma) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bs = BS > 0 ? BS : S.bs;
+    const int T = S.T, h = S.T / 2, bb = bs * bs;
+    SolverCtx C;
+    C.sm = smem_u32(smem_raw);
+    C.oDinv = S.oDinv; C.oOff = S.oOff; C.oRHS = S.oRHS;
+    C.oV = S.oV + warp * 256; C.oScr = S.oScr + warp * bb * 8;
+    C.oOffCol = S.oOffCol; C.oOffTrow = S.oOffTrow; C.oOffTslot = S.oOffTslot;
+    C.bs = bs; C.T = T; C.ow = S.ow; C.owT = S.owT;
+    for (;;) {
+        __syncthreads(); // (E) control word + inputs published
+        const int ctrl = *sCtrl;
+        if (ctrl == CTRL_EXIT) break;
+        if (ctrl == CTRL_FACTOR) {
+            assemble_S(S, sigma, sW, sA, sP, sDinv, sOff, tid, bs);
+            __syncthreads(); // (B) S assembled
+            factor_cooperative<BS>(S, smem_raw, tid, 0);
+            __syncthreads(); // (C) both halves eliminated
+            factor_cooperative<BS>(S, smem_raw, tid, 1);
+            __syncthreads(); // (D) factor complete
+            continue;
+        }
+        // block-tridiagonal solve, in place on sRHS
+        if (BS > 0 && S.ow <= 2 && S.owT <= 2) {
+            // ---- fast path: previous stage's result carried in registers, one __syncwarp per step
+            const int rl = lane < bs ? lane : bs - 1;
+            OffPattern pat;
+            if (T > 1) load_off_pattern(C, 0, rl, pat); // reused for every stage when the pattern is uniform
+            if (warp == 0) { // stages 0 .. h-1 forward, the middle stage, then back up
+                double u = 0.0;
+#pragma unroll 1
+                for (int t = 0; t < h; ++t) {
+                    if (!S.uniform_off && t > 0) load_off_pattern(C, t - 1, rl, pat);
+                    u = chain_step<BS>(C, t, t - 1, false, true, u, lane, pat);
+                }
+                __syncwarp();
+                named_bar_sync(1, 64);
+                double yv = lane < bs ? sRHS[h * bs + lane] : 0.0;
+                if (lane < bs) {
+                    if (h > 0) yv -= off_mul(C, h - 1, sRHS + (h - 1) * bs, lane);
+                    if (h < T - 1) yv -= offT_mul(C, h, sRHS + (h + 1) * bs, lane);
+                }
+                double xv = apply_dinv<BS>(C, h, yv, lane);
+                if (lane < bs) sRHS[h * bs + lane] = xv;
+                named_bar_sync(2, 64);
+#pragma unroll 1
+                for (int t = h - 1; t >= 0; --t) { // x_t = u_t - Dinv_t Off_t' x_{t+1}
+                    if (!S.uniform_off) load_off_pattern(C, t, rl, pat);
+                    xv = chain_step<BS>(C, t, t, true, false, xv, lane, pat);
+                }
+            } else { // stages T-1 .. h+1 forward (upwards), then back down
+                double u = 0.0;
+#pragma unroll 1
+                for (int t = T - 1; t > h; --t) {
+                    if (!S.uniform_off && t < T - 1) load_off_pattern(C, t, rl, pat);
+                    u = chain_step<BS>(C, t, t < T - 1 ? t : -1, true, true, u, lane, pat);
+                }
+                __syncwarp();
+                named_bar_sync(1, 64);
+                named_bar_sync(2, 64);
+                double xv = sRHS[h * bs + rl];
+#pragma unroll 1
+                for (int t = h + 1; t < T; ++t) { // x_t = u_t - Dinv_t Off_{t-1} x_{t-1}
+                    if (!S.uniform_off) load_off_pattern(C, t - 1, rl, pat);
+                    xv = chain_step<BS>(C, t, t - 1, false, false, xv, lane, pat);
+                }
+            }
+        } else
+        if (warp == 0) { // stages 0 .. h-1 forward, the middle stage, then back up
+            for (int t = 0; t < h; ++t) {
+                double yv = lane < bs ? sRHS[t * bs + lane] : 0.0;
+                if (t > 0 && lane < bs) yv -= off_mul(C, t - 1, sRHS + (t - 1) * bs, lane);
+                const double u = apply_dinv<BS>(C, t, yv, lane);
+                if (lane < bs) sRHS[t * bs + lane] = u;
+                __syncwarp();
+            }
+            named_bar_sync(1, 64);
+            double yv = lane < bs ? sRHS[h * bs + lane] : 0.0;
+            if (lane < bs) {
+                if (h > 0) yv -= off_mul(C, h - 1, sRHS + (h - 1) * bs, lane);
+                if (h < T - 1) yv -= offT_mul(C, h, sRHS + (h + 1) * bs, lane);
+            }
+            const double xm = apply_dinv<BS>(C, h, yv, lane);
+            if (lane < bs) sRHS[h * bs + lane] = xm;
+            named_bar_sync(2, 64);
+            for (int t = h - 1; t >= 0; --t) { // x_t = u_t - Dinv_t Off_t' x_{t+1}
+                const double v = lane < bs ? offT_mul(C, t, sRHS + (t + 1) * bs, lane) : 0.0;
+                const double corr = apply_dinv<BS>(C, t, v, lane);
+                if (lane < bs) sRHS[t * bs + lane] -= corr;
+                __syncwarp();
+            }
+        } else { // stages T-1 .. h+1 forward (upwards), then back down
+            for (int t = T - 1; t > h; --t) {
+                double yv = lane < bs ? sRHS[t * bs + lane] : 0.0;
+                if (t < T - 1 && lane < bs) yv -= offT_mul(C, t, sRHS + (t + 1) * bs, lane);
+                const double u = apply_dinv<BS>(C, t, yv, lane);
+                if (lane < bs) sRHS[t * bs + lane] = u;
+                __syncwarp();
+            }
+            named_bar_sync(1, 64);
+            named_bar_sync(2, 64);
+            for (int t = h + 1; t < T; ++t) { // x_t = u_t - Dinv_t Off_{t-1} x_{t-1}
+                const double v = lane < bs ? off_mul(C, t - 1, sRHS + (t - 1) * bs, lane) : 0.0;
+                const double corr = apply_dinv<BS>(C, t, v, lane);
+                if (lane < bs) sRHS[t * bs + lane] -= corr;
+                __syncwarp();
+            }
+        }
+        __syncthreads(); // (F) x~ ready
+    }
+}
+
+template <int RPT, int CPT, int BS>
+__global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_constant__ DevSym S, const __grid_constant__ DevBatch B,
+                                                                const __grid_constant__ DevSettings st) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool owner = tid >= kSolverThreads;
+    const int oid = tid - kSolverThreads;
+    const int bs = BS > 0 ? BS : S.bs;
+    const int T = S.T, np = S.n_pad, mu = S.m_used, h = S.T / 2, bb = bs * bs;
+
     // ---- once per kernel: sparsity pattern -> shared memory (identical for every QP of the batch)
     for (int k = tid; k < S.nnzA; k += kThreads) {
         sRowEnt[k] = S.row_csr[k];
         sCscRow[k] = S.csc_row[k];
     }
     for (int k = tid; k < np; k += kThreads) sColRange[k] = S.col_range[k];
-    for (int k = tid; k <= mu; k += kThreads) sRowPtr[k] = S.row_ptr[k];
-    for (int k = tid; k < S.npf; k += kThreads) sPfEnt[k] = S.pf_csr[k];
-    for (int k = tid; k <= np; k += kThreads) sPfPtr[k] = S.pf_ptr[k];
-    for (int k = tid; k < S.nnzPu; k += kThreads) sPuIJ[k] = S.Pu_ij[k];
+    for (int k = tid; k < mu; k += kThreads) sRowRange[k] = S.row_range[k];
+    if (tid < 4) sRowEnt[S.nnzA + tid] = 0u; // the 4-wide entry loops may read past the last row
+    // P-side patterns are only touched by the scaling and the residual phases: shared memory if there is room
+    const uint32_t *sPfEnt = S.pf_csr, *sPuIJ = S.Pu_ij;
+    const uint16_t *sPfPtr = S.pf_ptr;
+    if (S.p_in_smem) {
+        uint32_t *e = reinterpret_cast<uint32_t *>(smem_raw + S.oPfEnt), *ij = reinterpret_cast<uint32_t *>(smem_raw + S.oPuIJ);
+        uint16_t *pp = reinterpret_cast<uint16_t *>(smem_raw + S.oPfPtr);
+        for (int k = tid; k < S.npf; k += kThreads) e[k] = S.pf_csr[k];
+        for (int k = tid; k <= np; k += kThreads) pp[k] = S.pf_ptr[k];
+        for (int k = tid; k < S.nnzPu; k += kThreads) ij[k] = S.Pu_ij[k];
+        sPfEnt = e;
+        sPuIJ = ij;
+        sPfPtr = pp;
+    }
     for (int k = tid; k < (T - 1) * bs * S.ow; k += kThreads) sOffCol[k] = S.off_col[k];
     for (int k = tid; k < (T - 1) * bs * S.owT; k += kThreads) {
         sOffTrow[k] = S.offT_row[k];
@@ -625,96 +712,9 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
         if (b >= B.batch) break;
 
         if (!owner) {
-            // =====================================================================================
-            // SOLVER warps: wait for the owners' control word, then factor or substitute.
-            // =====================================================================================
-            SolverCtx C;
-            C.sm = smem_u32(smem_raw);
-            C.oDinv = S.oDinv; C.oOff = S.oOff; C.oRHS = S.oRHS;
-            C.oV = S.oV + warp * 256; C.oScr = S.oScr + warp * bb * 8;
-            C.oOffCol = S.oOffCol; C.oOffTrow = S.oOffTrow; C.oOffTslot = S.oOffTslot;
-            C.bs = bs; C.T = T; C.ow = S.ow; C.owT = S.owT;
-            for (;;) {
-                __syncthreads(); // (E) control word + inputs published
-                const int ctrl = *sCtrl;
-                if (ctrl == CTRL_EXIT) break;
-                if (ctrl == CTRL_FACTOR) {
-                    assemble_S(S, st.sigma, sW, sA, sP, sDinv, sOff, tid, bs);
-                    __syncthreads(); // (B) S assembled
-                    factor_cooperative<BS>(S, smem_raw, tid, 0);
-                    __syncthreads(); // (C) both halves eliminated
-                    factor_cooperative<BS>(S, smem_raw, tid, 1);
-                    __syncthreads(); // (D) factor complete
-                    continue;
-                }
-                // block-tridiagonal solve, in place on sRHS
-                if (BS > 0 && S.ow <= 2 && S.owT <= 2) {
-                    // ---- fast path: per step, everything independent of the previous stage is loaded first
-                    if (warp == 0) { // stages 0 .. h-1 forward, the middle stage, then back up
-#pragma unroll 1
-                        for (int t = 0; t < h; ++t) chain_step<BS>(C, t, t - 1, false, t > 0 ? t - 1 : 0, true, lane);
-                        named_bar_sync(1, 64);
-                        double yv = lane < bs ? sRHS[h * bs + lane] : 0.0;
-                        if (lane < bs) {
-                            if (h > 0) yv -= off_mul(C, h - 1, sRHS + (h - 1) * bs, lane);
-                            if (h < T - 1) yv -= offT_mul(C, h, sRHS + (h + 1) * bs, lane);
-                        }
-                        const double xm = apply_dinv<BS>(C, h, yv, lane);
-                        if (lane < bs) sRHS[h * bs + lane] = xm;
-                        named_bar_sync(2, 64);
-#pragma unroll 1
-                        for (int t = h - 1; t >= 0; --t) chain_step<BS>(C, t, t, true, t + 1, false, lane); // x_t = u_t - Dinv_t Off_t' x_{t+1}
-                    } else { // stages T-1 .. h+1 forward (upwards), then back down
-#pragma unroll 1
-                        for (int t = T - 1; t > h; --t) chain_step<BS>(C, t, t < T - 1 ? t : -1, true, t < T - 1 ? t + 1 : t, true, lane);
-                        named_bar_sync(1, 64);
-                        named_bar_sync(2, 64);
-#pragma unroll 1
-                        for (int t = h + 1; t < T; ++t) chain_step<BS>(C, t, t - 1, false, t - 1, false, lane); // x_t = u_t - Dinv_t Off_{t-1} x_{t-1}
-                    }
-                } else
-                if (warp == 0) { // stages 0 .. h-1 forward, the middle stage, then back up
-                    for (int t = 0; t < h; ++t) {
-                        double yv = lane < bs ? sRHS[t * bs + lane] : 0.0;
-                        if (t > 0 && lane < bs) yv -= off_mul(C, t - 1, sRHS + (t - 1) * bs, lane);
-                        const double u = apply_dinv<BS>(C, t, yv, lane);
-                        if (lane < bs) sRHS[t * bs + lane] = u;
-                        __syncwarp();
-                    }
-                    named_bar_sync(1, 64);
-                    double yv = lane < bs ? sRHS[h * bs + lane] : 0.0;
-                    if (lane < bs) {
-                        if (h > 0) yv -= off_mul(C, h - 1, sRHS + (h - 1) * bs, lane);
-                        if (h < T - 1) yv -= offT_mul(C, h, sRHS + (h + 1) * bs, lane);
-                    }
-                    const double xm = apply_dinv<BS>(C, h, yv, lane);
-                    if (lane < bs) sRHS[h * bs + lane] = xm;
-                    named_bar_sync(2, 64);
-                    for (int t = h - 1; t >= 0; --t) { // x_t = u_t - Dinv_t Off_t' x_{t+1}
-                        const double v = lane < bs ? offT_mul(C, t, sRHS + (t + 1) * bs, lane) : 0.0;
-                        const double corr = apply_dinv<BS>(C, t, v, lane);
-                        if (lane < bs) sRHS[t * bs + lane] -= corr;
-                        __syncwarp();
-                    }
-                } else { // stages T-1 .. h+1 forward (upwards), then back down
-                    for (int t = T - 1; t > h; --t) {
-                        double yv = lane < bs ? sRHS[t * bs + lane] : 0.0;
-                        if (t < T - 1 && lane < bs) yv -= offT_mul(C, t, sRHS + (t + 1) * bs, lane);
-                        const double u = apply_dinv<BS>(C, t, yv, lane);
-                        if (lane < bs) sRHS[t * bs + lane] = u;
-                        __syncwarp();
-                    }
-                    named_bar_sync(1, 64);
-                    named_bar_sync(2, 64);
-                    for (int t = h + 1; t < T; ++t) { // x_t = u_t - Dinv_t Off_{t-1} x_{t-1}
-                        const double v = lane < bs ? off_mul(C, t - 1, sRHS + (t - 1) * bs, lane) : 0.0;
-                        const double corr = apply_dinv<BS>(C, t, v, lane);
-                        if (lane < bs) sRHS[t * bs + lane] -= corr;
-                        __syncwarp();
-                    }
-                }
-                __syncthreads(); // (F) x~ ready
-            }
+            // SOLVER warps: wait for the owners' control word, then factor or substitute (separate function:
+            // its registers are allocated independently of the owner role's long-lived state)
+            solver_role<BS>(S, st.sigma);
             fence_proxy_async();
             continue;
         }
@@ -738,12 +738,15 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
         }
         for (int k = oid; k < S.nnzPu; k += kOwners) sP[k] = S.Pu_val[k];
         const double *gl = B.l + (size_t)b * S.m, *gu = B.u + (size_t)b * S.m;
-        double z[RPT], y[RPT], lo[RPT], hi[RPT];
+        // scaled bounds: shared memory when they fit, else this QP's slice of a global scratch (L2-resident)
+        double *const sLo = S.bounds_in_smem ? reinterpret_cast<double *>(smem_raw + S.oLo) : B.Lg + bmu;
+        double *const sHi = S.bounds_in_smem ? reinterpret_cast<double *>(smem_raw + S.oHi) : B.Ug + bmu;
+        double z[RPT], y[RPT]; // bounds live in shared memory (sLo, sHi): 2 loads per row and iteration, 4*RPT fewer registers
         double x[CPT];
         ROWS_LOOP(j, i) {
             const int orig = S.used_rows[i];
-            lo[j] = fmax(gl[orig], -kInfty); // osqp-cpp clips bounds to +-OSQP_INFTY
-            hi[j] = fmin(gu[orig], kInfty);
+            sLo[i] = fmax(gl[orig], -kInfty); // osqp-cpp clips bounds to +-OSQP_INFTY
+            sHi[i] = fmin(gu[orig], kInfty);
         }
         double bad[1] = {0.0};
         for (int e = oid; e < S.n_empty; e += kOwners) {
@@ -816,8 +819,8 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
                 owners_sync();
             }
             ROWS_LOOP(j, i) {
-                lo[j] *= Ei[j];
-                hi[j] *= Ei[j];
+                sLo[i] *= Ei[j];
+                sHi[i] *= Ei[j];
                 B.Eg[bmu + i] = Ei[j];
             }
             COLS_LOOP(c, p) {
@@ -833,8 +836,8 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
         unsigned ctype = 0; // 2 bits per owned row: 0 inequality, 1 equality, 2 loose
         ROWS_LOOP(j, i) {
             unsigned t = 0;
-            if (lo[j] < -kInfty * kMinScaling && hi[j] > kInfty * kMinScaling) t = 2;
-            else if (hi[j] - lo[j] < kRhoTol) t = 1;
+            if (sLo[i] < -kInfty * kMinScaling && sHi[i] > kInfty * kMinScaling) t = 2;
+            else if (sHi[i] - sLo[i] < kRhoTol) t = 1;
             ctype |= t << (2 * j);
         }
 
@@ -864,9 +867,7 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
             }
             owners_sync();
             ROWS_LOOP(j, i) {
-                double acc = 0.0;
-                ROW_ENTRIES(i, e) acc = fma(sA[e & 0xFFFFu], sRHS[e >> 16], acc);
-                z[j] = acc;
+                z[j] = row_dot4(sRowEnt, sRowRange[i], sA, sRHS);
             }
             owners_sync();
         }
@@ -915,8 +916,7 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
             COLS_LOOP(c, p) {
                 double acc = st.sigma * x[c];
                 if (hasq) acc -= B.qs[bnp + p];
-                COL_ENTRIES(p, k) acc = fma(sA[k], sW[sCscRow[k]], acc);
-                sRHS[p] = acc;
+                sRHS[p] = col_dot4(sColRange[p], sA, sCscRow, sW, acc);
             }
             if (oid == 0) *sCtrl = CTRL_SOLVE;
             PHASE_MARK(PH_RHS);
@@ -935,11 +935,10 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
                 x[c] = xn;
             }
             ROWS_LOOP(j, i) {
-                double zt = 0.0;
-                ROW_ENTRIES(i, e) zt = fma(sA[e & 0xFFFFu], sRHS[e >> 16], zt);
+                const double zt = row_dot4(sRowEnt, sRowRange[i], sA, sRHS);
                 const unsigned t = (ctype >> (2 * j)) & 3u;
                 const double zr = st.alpha * zt + (1.0 - st.alpha) * z[j];
-                const double zn = fmin(fmax(zr + RINV_OF(t) * y[j], lo[j]), hi[j]);
+                const double zn = fmin(fmax(zr + RINV_OF(t) * y[j], sLo[i]), sHi[i]);
                 const double d = RHO_OF(t) * (zr - zn);
                 y[j] += d;
                 z[j] = zn;
@@ -951,44 +950,50 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
 
             if (do_info) {
                 // ---------------- residuals and the norms OSQP's tolerances need (update_info)
-                double nv[kRedK];
                 COLS_LOOP(c, p) sRHS[p] = x[c];
                 ROWS_LOOP(j, i) sW[i] = y[j];
                 w_dirty = true;
                 owners_sync();
-#pragma unroll
-                for (int k = 0; k < kRedK; ++k) nv[k] = 0.0;
-                ROWS_LOOP(j, i) {
-                    double ax = 0.0;
-                    ROW_ENTRIES(i, e) ax = fma(sA[e & 0xFFFFu], sRHS[e >> 16], ax);
-                    const double pr = ax - z[j];
-                    const double einv = 1.0 / B.Eg[bmu + i];
-                    nv[0] = fmax(nv[0], fabs(einv * pr));
-                    nv[1] = fmax(nv[1], fabs(pr));
-                    nv[2] = fmax(nv[2], fabs(einv * z[j]));
-                    nv[3] = fmax(nv[3], fabs(einv * ax));
-                    nv[4] = fmax(nv[4], fabs(z[j]));
-                    nv[5] = fmax(nv[5], fabs(ax));
+                double pri_u, pri_s, pn_u, pn_s, dua_u, dua_s, dn_u, dn_s; // residuals / normalisers, unscaled and scaled
+                {
+                    double na[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                    ROWS_LOOP(j, i) {
+                        const double ax = row_dot4(sRowEnt, sRowRange[i], sA, sRHS);
+                        const double pr = ax - z[j];
+                        const double einv = 1.0 / B.Eg[bmu + i];
+                        na[0] = fmax(na[0], fabs(einv * pr));
+                        na[1] = fmax(na[1], fabs(pr));
+                        na[2] = fmax(na[2], fabs(einv * z[j]));
+                        na[3] = fmax(na[3], fabs(einv * ax));
+                        na[4] = fmax(na[4], fabs(z[j]));
+                        na[5] = fmax(na[5], fabs(ax));
+                    }
+                    owners_max<6>(na, sRed, oid);
+                    pri_u = na[0]; pri_s = na[1]; pn_u = fmax(na[2], na[3]); pn_s = fmax(na[4], na[5]);
                 }
-                COLS_LOOP(c, p) {
-                    double px = 0.0, aty = 0.0;
-                    PF_ENTRIES(p, e) px = fma(sP[e & 0xFFFFu], sRHS[e >> 16], px);
-                    COL_ENTRIES(p, k) aty = fma(sA[k], sW[sCscRow[k]], aty);
-                    const double qq = hasq ? B.qs[bnp + p] : 0.0;
-                    const double du = qq + px + aty;
-                    const double dinv = 1.0 / B.Dg[bnp + p];
-                    nv[6] = fmax(nv[6], fabs(dinv * du));
-                    nv[7] = fmax(nv[7], fabs(du));
-                    nv[8] = fmax(nv[8], fabs(dinv * px));
-                    nv[9] = fmax(nv[9], fabs(dinv * aty));
-                    nv[10] = fmax(nv[10], fabs(dinv * qq));
-                    nv[11] = fmax(nv[11], fabs(px));
-                    nv[12] = fmax(nv[12], fabs(aty));
-                    nv[13] = fmax(nv[13], fabs(qq));
+                {
+                    double nb[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                    COLS_LOOP(c, p) {
+                        double px = 0.0;
+                        PF_ENTRIES(p, e) px = fma(sP[e & 0xFFFFu], sRHS[e >> 16], px);
+                        const double aty = col_dot4(sColRange[p], sA, sCscRow, sW, 0.0);
+                        const double qq = hasq ? B.qs[bnp + p] : 0.0;
+                        const double du = qq + px + aty;
+                        const double dinv = 1.0 / B.Dg[bnp + p];
+                        nb[0] = fmax(nb[0], fabs(dinv * du));
+                        nb[1] = fmax(nb[1], fabs(du));
+                        nb[2] = fmax(nb[2], fabs(dinv * px));
+                        nb[3] = fmax(nb[3], fabs(dinv * aty));
+                        nb[4] = fmax(nb[4], fabs(dinv * qq));
+                        nb[5] = fmax(nb[5], fabs(px));
+                        nb[6] = fmax(nb[6], fabs(aty));
+                        nb[7] = fmax(nb[7], fabs(qq));
+                    }
+                    owners_max<8>(nb, sRed, oid);
+                    dua_u = nb[0]; dua_s = nb[1]; dn_u = fmax(nb[4], fmax(nb[3], nb[2])); dn_s = fmax(nb[7], fmax(nb[6], nb[5]));
                 }
-                owners_max<kRedK>(nv, sRed, oid);
-                pri_res = uns ? nv[0] : nv[1];
-                dua_res = uns ? cinv * nv[6] : nv[7];
+                pri_res = uns ? pri_u : pri_s;
+                dua_res = uns ? cinv * dua_u : dua_s;
                 iters_done = iter;
 
                 // ---------------- termination: stage 0 exact tolerances, stage 1 (only at max_iter) 10x tolerances
@@ -998,8 +1003,8 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
                     if (stage == 0 && !(can_check || last)) continue;
                     if (stage == 1) {
                         if (adapt_now) { // OSQP adapt_rho: estimate from the scaled residuals
-                            const double pr = nv[1] / (fmax(nv[4], nv[5]) + kDivTol);
-                            const double dr = nv[7] / (fmax(nv[13], fmax(nv[12], nv[11])) + kDivTol);
+                            const double pr = pri_s / (pn_s + kDivTol);
+                            const double dr = dua_s / (dn_s + kDivTol);
                             const double est = fmin(fmax(rho * sqrt(pr / dr), kRhoMin), kRhoMax);
                             if (est > rho * st.adaptive_rho_tolerance || est < rho / st.adaptive_rho_tolerance) {
                                 rho = est;
@@ -1023,41 +1028,38 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
                         ea *= 10; er *= 10; epi *= 10; edi *= 10;
                     }
                     bool prc = false, drc = false, pic = false, dic = false;
-                    const double eps_prim = ea + er * (uns ? fmax(nv[2], nv[3]) : fmax(nv[4], nv[5]));
+                    const double eps_prim = ea + er * (uns ? pn_u : pn_s);
                     if (mu == 0 || pri_res < eps_prim) {
                         prc = true;
                     } else {
-                        // OSQP is_primal_infeasible on delta_y
-                        double dyr[RPT];
+                        // OSQP is_primal_infeasible on delta_y (projected onto the polar of the recession cone, kept in sW)
                         double nrm[1] = {0.0}, lhs = 0.0;
                         ROWS_LOOP(j, i) {
                             double d = B.dyg[bmu + i];
-                            if (hi[j] > kInfty * kMinScaling) {
-                                if (lo[j] < -kInfty * kMinScaling) d = 0.0;
+                            const double l_ = sLo[i], u_ = sHi[i];
+                            if (u_ > kInfty * kMinScaling) {
+                                if (l_ < -kInfty * kMinScaling) d = 0.0;
                                 else d = fmin(d, 0.0);
-                            } else if (lo[j] < -kInfty * kMinScaling) {
+                            } else if (l_ < -kInfty * kMinScaling) {
                                 d = fmax(d, 0.0);
                             }
-                            dyr[j] = d;
+                            sW[i] = d;
                             nrm[0] = fmax(nrm[0], fabs(uns ? B.Eg[bmu + i] * d : d));
-                            lhs += hi[j] * fmax(d, 0.0) + lo[j] * fmin(d, 0.0);
+                            lhs += u_ * fmax(d, 0.0) + l_ * fmin(d, 0.0);
                         }
-                        owners_max<1>(nrm, sRed, oid);
+                        owners_max<1>(nrm, sRed, oid); // (also orders the sW writes before the gather below)
                         lhs = owners_sum(lhs, sRed, oid);
                         if (nrm[0] > kDivTol && lhs < -epi * nrm[0]) {
-                            ROWS_LOOP(j, i) sW[i] = dyr[j];
-                            owners_sync();
                             double v[1] = {0.0};
                             COLS_LOOP(c, p) {
-                                double acc = 0.0;
-                                COL_ENTRIES(p, k) acc = fma(sA[k], sW[sCscRow[k]], acc);
+                                const double acc = col_dot4(sColRange[p], sA, sCscRow, sW, 0.0);
                                 v[0] = fmax(v[0], fabs(uns ? (1.0 / B.Dg[bnp + p]) * acc : acc));
                             }
                             owners_max<1>(v, sRed, oid);
                             pic = v[0] < epi * nrm[0];
                         }
                     }
-                    const double mx = uns ? cinv * fmax(nv[10], fmax(nv[9], nv[8])) : fmax(nv[13], fmax(nv[12], nv[11]));
+                    const double mx = uns ? cinv * dn_u : dn_s;
                     const double eps_dual = ea + er * mx;
                     if (dua_res < eps_dual) {
                         drc = true;
@@ -1085,11 +1087,10 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
                             if (v[0] < cs_ * edi * nrm[0]) {
                                 double viol[1] = {0.0};
                                 ROWS_LOOP(j, i) {
-                                    double acc = 0.0;
-                                    ROW_ENTRIES(i, e) acc = fma(sA[e & 0xFFFFu], sRHS[e >> 16], acc);
+                                    double acc = row_dot4(sRowEnt, sRowRange[i], sA, sRHS);
                                     if (uns) acc *= 1.0 / B.Eg[bmu + i];
-                                    if ((hi[j] < kInfty * kMinScaling && acc > edi * nrm[0]) ||
-                                        (lo[j] > -kInfty * kMinScaling && acc < -edi * nrm[0]))
+                                    if ((sHi[i] < kInfty * kMinScaling && acc > edi * nrm[0]) ||
+                                        (sLo[i] > -kInfty * kMinScaling && acc < -edi * nrm[0]))
                                         viol[0] = 1.0;
                                 }
                                 owners_max<1>(viol, sRed, oid);
@@ -1153,13 +1154,10 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const DevSym S, 
 #undef sDinv
 #undef sOff
 #undef sRed
+#undef sRowRange
 #undef sRowEnt
 #undef sColRange
-#undef sPfEnt
-#undef sPuIJ
-#undef sRowPtr
 #undef sCscRow
-#undef sPfPtr
 #undef sOffTslot
 #undef sOffCol
 #undef sOffTrow

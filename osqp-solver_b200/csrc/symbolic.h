@@ -57,6 +57,7 @@ struct Symbolic {
     // compact views staged into shared memory by the kernel
     std::vector<uint16_t> row_ptr;   // [m_used + 1] CSR pointers over compact rows
     std::vector<uint32_t> row_csr;   // [nnzA] (pos << 16 | k), row-major
+    std::vector<uint32_t> row_range; // [m_used] (first entry << 8 | length) into row_csr
     std::vector<uint16_t> csc_row;   // [nnzA] compact row of CSC entry k
     std::vector<uint32_t> col_range; // [n_pad] (start << 8 | len) of position p in the CSC value array
     std::vector<uint16_t> pf_ptr;    // [n_pad + 1] CSR pointers of the full-symmetric view of P
@@ -266,7 +267,9 @@ inline bool analyse(Symbolic &sym, int64_t n, int64_t m, const int64_t *Pp, cons
         }
         sym.row_ptr.assign((size_t)sym.m_used + 1, 0);
         sym.row_csr.clear();
+        sym.row_range.assign((size_t)sym.m_used, 0);
         for (int i = 0; i < sym.m_used; ++i) {
+            sym.row_range[(size_t)i] = ((uint32_t)sym.row_csr.size() << 8) | (uint32_t)ent[(size_t)i].size();
             for (uint32_t e : ent[(size_t)i]) sym.row_csr.push_back(e);
             sym.row_ptr[(size_t)i + 1] = (uint16_t)sym.row_csr.size();
         }
