@@ -95,7 +95,7 @@ def workload(pkg):
                         "(eps 1e-3, adaptive_rho_interval pinned to 25)",
             "n_dim": 7, "waypoints": 50, "n": pat.n, "m": pat.m, "nnzA": pat.nnzA, "batch_per_gpu": BATCH_PER_GPU,
             "l2_policy": "inputs larger than L2 (305 MB of A_val/l/u per step vs 126 MB L2)",
-            "batches_in_flight": 2}
+            "batches_in_flight": 4}
     return cfg, pat, desc
 
 
@@ -155,10 +155,10 @@ def run_gpu(args):
             dict(A_val=(B, pat.nnzA), l=(B, pat.m), u=(B, pat.m), x0=(B, pat.n), start_goal=(B, 2 * cfg.n_dim)).items()}
     pkg.problem.generate(pat, first_id, B, out={k: v.numpy() for k, v in host.items()})
     dev = {k: host[k].cuda() for k in ("A_val", "l", "u", "x0")}
-    # Two batches in flight: consecutive steps alternate between two handles on two streams, so the few
+    # Four batches in flight: consecutive steps rotate over four handles on four streams, so the few
     # QPs of a batch that need thousands of ADMM iterations (max_iter = 4000) overlap with the next batch
     # instead of leaving 146 SMs idle.  Every step still is a full cold setup + warm start + solve.
-    PIPE = 2
+    PIPE = 4
     streams = [torch.cuda.Stream() for _ in range(PIPE)]
     main = torch.cuda.current_stream()
 

@@ -109,6 +109,7 @@ typedef struct gomp_info {
     int64_t flops_per_check, smem_bytes_per_check;
     double phase_cycles[8];        /* with env GOMP_PROFILE_PHASES=1 at create: SM cycles summed over all QPs per phase
                                       (load, scaling, factor, rhs gather, block solve, x/z/y update, residuals+termination, store) */
+    double chain_cycles;           /* cycles warp 0 spends in the block substitutions proper (inside phase_cycles[4]) */
     double assemble_cycles;        /* part of phase_cycles[2] spent assembling S (all threads) */
 } gomp_info;
 

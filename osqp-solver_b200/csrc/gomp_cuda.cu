@@ -707,6 +707,9 @@ int gomp_batch_info(gomp_batch *h, gomp_info *info) {
             for (int k = 0; k < 8; ++k) info->phase_cycles[k] = (double)pc[k];
             info->phase_cycles[2] += (double)pc[8]; // assembly is reported inside 'factor'
             info->assemble_cycles = (double)pc[8];
+            info->chain_cycles = (double)pc[9];
+            if (std::getenv("GOMP_PROFILE_PHASES")[0] == '2')
+                std::fprintf(stderr, "chain marks (cumulative cycles): fwd %.0f, after bar1 %.0f, after middle+bar2 %.0f, total %.0f\n", (double)pc[10], (double)pc[11], (double)pc[12], (double)pc[9]);
     }
     info->last_solve_ms = h->last_solve_ms;
     info->last_h2d_ms = h->last_h2d_ms;

@@ -313,7 +313,7 @@ __device__ __forceinline__ double chain_step(const SolverCtx &C, int t, int tb, 
 //                                        the ADMM kernel
 // ================================================================================================
 // phase timers: thread 0 accumulates clock64() deltas per phase when B.prof is set
-enum { PH_LOAD = 0, PH_SCALE, PH_FACTOR, PH_RHS, PH_SOLVE, PH_UPDATE, PH_INFO, PH_STORE, PH_ASSEMBLE, PH_COUNT };
+enum { PH_LOAD = 0, PH_SCALE, PH_FACTOR, PH_RHS, PH_SOLVE, PH_UPDATE, PH_INFO, PH_STORE, PH_ASSEMBLE, PH_CHAIN, PH_COUNT };
 #define PHASE_MARK(ph)                                                              \
     do {                                                                            \
         if (B.prof != nullptr && tid == kSolverThreads) {                           \
@@ -335,6 +335,81 @@ enum { PH_LOAD = 0, PH_SCALE, PH_FACTOR, PH_RHS, PH_SOLVE, PH_UPDATE, PH_INFO, P
 #define PF_ENTRIES(p, e) \
     for (int q__ = sPfPtr[p], q1__ = sPfPtr[(p) + 1]; q__ < q1__; ++q__) \
         if (const uint32_t e = sPfEnt[q__]; true)
+
+// ---- raw shared-memory accessors (32-bit shared-window addresses): the substitution sweeps below are
+// latency-critical single-warp code, so their loads/stores are written out explicitly
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
+// One substitution sweep over `count` stages starting at stage t0 and moving by dir (+1 / -1), in place on rhs.
+//   fwd:  rhs_t <- Dinv_t (rhs_t - O . prev)      bwd:  rhs_t <- rhs_t - Dinv_t (O . prev)
+// where prev is the previous stage's result (kept in a register per lane, gathered with two shuffles) and O
+// is the off-diagonal block tb = t + tbo (its transpose when the per-lane offsets describe a column).
+// Per-lane pattern constants (uniform over the stages): g0/g1 source lanes, o0/o1 byte offsets of the two
+// values inside block tb, has0/has1.  Returns the last stage's result.
+template <int BS>
+__device__ __forceinline__ double chain_sweep(uint32_t dinv0, uint32_t rhs0, uint32_t off0, uint32_t vb0, int t0, int count, int dir,
+                                              int tbo, int nblk, uint32_t blk_bytes, bool fwd, double prev, int lane, int g0, int g1,
+                                              uint32_t o0, uint32_t o1, bool has0, bool has1) {
+    constexpr int NB = BS > 0 ? BS : 2;
+    const int rl = lane < NB ? lane : NB - 1;
+    const bool act = lane < NB;
+    int t = t0;
+#pragma unroll 1
+    for (int it = 0; it < count; ++it, t += dir) {
+        // ---- independent of the previous stage: row of the inverted pivot block, rhs entry, off-diagonal values
+        const uint32_t arow = dinv0 + (uint32_t)((t * NB + rl) * NB) * 8u;
+        double m[NB];
+#pragma unroll
+        for (int c = 0; c < NB; c += 2) {
+            const double2 d = lds_f64x2(arow + (uint32_t)c * 8u);
+            m[c] = d.x;
+            m[c + 1] = d.y;
+        }
+        const uint32_t ab = rhs0 + (uint32_t)(t * NB + rl) * 8u;
+        const double b = lds_f64(ab);
+        const int tb = t + tbo;
+        const bool blk = tb >= 0 && tb < nblk;
+        const uint32_t ao = off0 + (uint32_t)(blk ? tb : 0) * blk_bytes;
+        const double ov0 = (blk && has0) ? lds_f64(ao + o0) : 0.0;
+        const double ov1 = (blk && has1) ? lds_f64(ao + o1) : 0.0;
+        // ---- dependent chain
+        const double up0 = __shfl_sync(0xffffffffu, prev, g0);
+        const double up1 = __shfl_sync(0xffffffffu, prev, g1);
+        const double off = fma(ov0, up0, ov1 * up1);
+        const double v = fwd ? b - off : off;
+        const uint32_t avb = vb0 + (uint32_t)(t & 1) * 128u;
+        if (act) sts_f64(avb + (uint32_t)lane * 8u, v);
+        __syncwarp();
+        double2 w[NB / 2]; // all broadcast loads in flight before the first FMA
+#pragma unroll
+        for (int c = 0; c < NB; c += 2) w[c / 2] = lds_f64x2(avb + (uint32_t)c * 8u);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int c = 0; c < NB; c += 2) {
+            if ((c >> 1) & 1) {
+                a2 = fma(m[c], w[c / 2].x, a2);
+                a3 = fma(m[c + 1], w[c / 2].y, a3);
+            } else {
+                a0 = fma(m[c], w[c / 2].x, a0);
+                a1 = fma(m[c + 1], w[c / 2].y, a1);
+            }
+        }
+        const double acc = (a0 + a1) + (a2 + a3);
+        prev = fwd ? acc : b - acc;
+        if (act) sts_f64(ab, prev);
+    }
+    return prev;
+}
 
 // ---- cooperative block factorisation -----------------------------------------------------------------
 // The two elimination chains (stages 0..h-1 downwards, T-1..h+1 upwards) are sequential over stages, and
@@ -453,15 +528,27 @@ __device__ __forceinline__ void factor_cooperative(const DevSym &S, unsigned cha
     }
 }
 
-// ---- sparse dot products of the owners, 4 entries in flight ---------------------------------------------
+// ---- sparse dot products of the owners ---------------------------------------------------------------------
 // row i of A times a dense vector in shared memory; `range` = (first entry << 8 | length), entries are
-// (position << 16 | value index).  The entry array is padded so that reading 3 entries past a row is legal;
-// the surplus products are never accumulated.
-__device__ __forceinline__ double row_dot4(const uint32_t *__restrict__ ent, uint32_t range, const double *__restrict__ A,
-                                           const double *__restrict__ vec) {
-    int q = (int)(range >> 8);
-    const int q1 = q + (int)(range & 0xFFu);
-    double acc = 0.0;
+// (position << 16 | value index).  The first four entries are loaded unconditionally (the entry array is
+// padded, surplus products are masked), so the loads of several rows of one thread can be issued together;
+// longer rows continue in row_rest4.
+__device__ __forceinline__ double row_first4(const uint32_t *__restrict__ ent, uint32_t range, const double *__restrict__ A,
+                                             const double *__restrict__ vec) {
+    const int q = (int)(range >> 8), len = (int)(range & 0xFFu);
+    const uint32_t e0 = ent[q], e1 = ent[q + 1], e2 = ent[q + 2], e3 = ent[q + 3];
+    const double a0 = A[e0 & 0xFFFFu], a1 = A[e1 & 0xFFFFu], a2 = A[e2 & 0xFFFFu], a3 = A[e3 & 0xFFFFu];
+    const double v0 = vec[e0 >> 16], v1 = vec[e1 >> 16], v2 = vec[e2 >> 16], v3 = vec[e3 >> 16];
+    double acc = len > 0 ? a0 * v0 : 0.0;
+    acc = len > 1 ? fma(a1, v1, acc) : acc;
+    acc = len > 2 ? fma(a2, v2, acc) : acc;
+    acc = len > 3 ? fma(a3, v3, acc) : acc;
+    return acc;
+}
+__device__ __forceinline__ double row_rest4(const uint32_t *__restrict__ ent, uint32_t range, const double *__restrict__ A,
+                                            const double *__restrict__ vec, double acc) {
+    int q = (int)(range >> 8) + 4;
+    const int q1 = (int)(range >> 8) + (int)(range & 0xFFu);
     for (; q < q1; q += 4) {
         const uint32_t e0 = ent[q], e1 = ent[q + 1], e2 = ent[q + 2], e3 = ent[q + 3];
         const double a0 = A[e0 & 0xFFFFu], a1 = A[e1 & 0xFFFFu], a2 = A[e2 & 0xFFFFu], a3 = A[e3 & 0xFFFFu];
@@ -471,6 +558,12 @@ __device__ __forceinline__ double row_dot4(const uint32_t *__restrict__ ent, uin
         if (q + 2 < q1) acc = fma(a2, v2, acc);
         if (q + 3 < q1) acc = fma(a3, v3, acc);
     }
+    return acc;
+}
+__device__ __forceinline__ double row_dot4(const uint32_t *__restrict__ ent, uint32_t range, const double *__restrict__ A,
+                                           const double *__restrict__ vec) {
+    double acc = row_first4(ent, range, A, vec);
+    if ((range & 0xFFu) > 4u) acc = row_rest4(ent, range, A, vec, acc);
     return acc;
 }
 // column of A (contiguous value range) times a row-indexed vector: sum_k A[k] * vec[rowOf[k]]
@@ -551,7 +644,7 @@ enum { CTRL_SOLVE = 0, CTRL_FACTOR = 1, CTRL_EXIT = 2 };
 //                       solver role (warps 0 and 1): one QP's linear algebra
 // ================================================================================================
 template <int BS>
-static __device__ __noinline__ void solver_role(const DevSym &S, double sigma) {
+static __device__ __noinline__ void solver_role(const DevSym &S, double sigma, unsigned long long *prof) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bs = BS > 0 ? BS : S.bs;
@@ -576,49 +669,46 @@ static __device__ __noinline__ void solver_role(const DevSym &S, double sigma) {
             continue;
         }
         // block-tridiagonal solve, in place on sRHS
-        if (BS > 0 && S.ow <= 2 && S.owT <= 2) {
-            // ---- fast path: previous stage's result carried in registers, one __syncwarp per step
+        const long long t_chain0 = clock64();
+        if (BS > 0 && S.uniform_off && S.ow <= 2 && S.owT <= 2) {
+            // ---- fast path (uniform off-diagonal pattern): register-carried stage results, explicit LDS/STS
             const int rl = lane < bs ? lane : bs - 1;
             OffPattern pat;
-            if (T > 1) load_off_pattern(C, 0, rl, pat); // reused for every stage when the pattern is uniform
-            if (warp == 0) { // stages 0 .. h-1 forward, the middle stage, then back up
-                double u = 0.0;
-#pragma unroll 1
-                for (int t = 0; t < h; ++t) {
-                    if (!S.uniform_off && t > 0) load_off_pattern(C, t - 1, rl, pat);
-                    u = chain_step<BS>(C, t, t - 1, false, true, u, lane, pat);
-                }
+            load_off_pattern(C, 0, rl, pat);
+            const uint32_t dinv0 = C.sm + (uint32_t)C.oDinv, rhs0 = C.sm + (uint32_t)C.oRHS, off0 = C.sm + (uint32_t)C.oOff,
+                           vb0 = C.sm + (uint32_t)C.oV;
+            const uint32_t blk_bytes = (uint32_t)(bs * C.ow) * 8u;
+            // forward pattern: row rl of Off_tb (values at (rl*ow + s));  transposed: column rl (values at the stored slots)
+            const int fg0 = pat.oi0 >= 0 ? pat.oi0 : 0, fg1 = pat.oi1 >= 0 ? pat.oi1 : 0;
+            const uint32_t fo0 = (uint32_t)(rl * C.ow) * 8u, fo1 = fo0 + 8u;
+            const bool fh0 = pat.oi0 >= 0, fh1 = pat.oi1 >= 0;
+            const int tg0 = pat.ti0 >= 0 ? pat.ti0 : 0, tg1 = pat.ti1 >= 0 ? pat.ti1 : 0;
+            const uint32_t to0 = (uint32_t)pat.ts0 * 8u, to1 = (uint32_t)pat.ts1 * 8u;
+            const bool th0 = pat.ti0 >= 0, th1 = pat.ti1 >= 0;
+            if (warp == 0) { // stages 0 .. h-1 forward (Off_{t-1} u_{t-1}), the middle stage, then back up (Off_t' x_{t+1})
+                const double u = chain_sweep<BS>(dinv0, rhs0, off0, vb0, 0, h, +1, -1, T - 1, blk_bytes, true, 0.0, lane, fg0, fg1, fo0, fo1, fh0, fh1);
+                (void)u;
                 __syncwarp();
+                if (prof != nullptr && tid == 0) atomicAdd(&prof[10], (unsigned long long)(clock64() - t_chain0));
                 named_bar_sync(1, 64);
+                if (prof != nullptr && tid == 0) atomicAdd(&prof[11], (unsigned long long)(clock64() - t_chain0));
                 double yv = lane < bs ? sRHS[h * bs + lane] : 0.0;
                 if (lane < bs) {
                     if (h > 0) yv -= off_mul(C, h - 1, sRHS + (h - 1) * bs, lane);
                     if (h < T - 1) yv -= offT_mul(C, h, sRHS + (h + 1) * bs, lane);
                 }
-                double xv = apply_dinv<BS>(C, h, yv, lane);
-                if (lane < bs) sRHS[h * bs + lane] = xv;
+                const double xm = apply_dinv<BS>(C, h, yv, lane);
+                if (lane < bs) sRHS[h * bs + lane] = xm;
                 named_bar_sync(2, 64);
-#pragma unroll 1
-                for (int t = h - 1; t >= 0; --t) { // x_t = u_t - Dinv_t Off_t' x_{t+1}
-                    if (!S.uniform_off) load_off_pattern(C, t, rl, pat);
-                    xv = chain_step<BS>(C, t, t, true, false, xv, lane, pat);
-                }
-            } else { // stages T-1 .. h+1 forward (upwards), then back down
-                double u = 0.0;
-#pragma unroll 1
-                for (int t = T - 1; t > h; --t) {
-                    if (!S.uniform_off && t < T - 1) load_off_pattern(C, t, rl, pat);
-                    u = chain_step<BS>(C, t, t < T - 1 ? t : -1, true, true, u, lane, pat);
-                }
+                if (prof != nullptr && tid == 0) atomicAdd(&prof[12], (unsigned long long)(clock64() - t_chain0));
+                chain_sweep<BS>(dinv0, rhs0, off0, vb0, h - 1, h, -1, 0, T - 1, blk_bytes, false, xm, lane, tg0, tg1, to0, to1, th0, th1);
+            } else { // stages T-1 .. h+1 forward (Off_t' u_{t+1}), then back down (Off_{t-1} x_{t-1})
+                chain_sweep<BS>(dinv0, rhs0, off0, vb0, T - 1, T - 1 - h, -1, 0, T - 1, blk_bytes, true, 0.0, lane, tg0, tg1, to0, to1, th0, th1);
                 __syncwarp();
                 named_bar_sync(1, 64);
                 named_bar_sync(2, 64);
-                double xv = sRHS[h * bs + rl];
-#pragma unroll 1
-                for (int t = h + 1; t < T; ++t) { // x_t = u_t - Dinv_t Off_{t-1} x_{t-1}
-                    if (!S.uniform_off) load_off_pattern(C, t - 1, rl, pat);
-                    xv = chain_step<BS>(C, t, t - 1, false, false, xv, lane, pat);
-                }
+                const double xm = sRHS[h * bs + rl];
+                chain_sweep<BS>(dinv0, rhs0, off0, vb0, h + 1, T - 1 - h, +1, -1, T - 1, blk_bytes, false, xm, lane, fg0, fg1, fo0, fo1, fh0, fh1);
             }
         } else
         if (warp == 0) { // stages 0 .. h-1 forward, the middle stage, then back up
@@ -661,6 +751,7 @@ static __device__ __noinline__ void solver_role(const DevSym &S, double sigma) {
                 __syncwarp();
             }
         }
+        if (prof != nullptr && tid == 0) atomicAdd(&prof[PH_CHAIN], (unsigned long long)(clock64() - t_chain0));
         __syncthreads(); // (F) x~ ready
     }
 }
@@ -714,7 +805,7 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_con
         if (!owner) {
             // SOLVER warps: wait for the owners' control word, then factor or substitute (separate function:
             // its registers are allocated independently of the owner role's long-lived state)
-            solver_role<BS>(S, st.sigma);
+            solver_role<BS>(S, st.sigma, B.prof);
             fence_proxy_async();
             continue;
         }
@@ -934,8 +1025,18 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_con
                 if (do_info && hasq) B.dxg[bnp + p] = xn - x[c];
                 x[c] = xn;
             }
+            // z~ = A x~ for all owned rows first (independent loads issued together), then the updates
+            uint32_t rng[RPT];
+            double ztv[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) rng[j] = oid + j * kOwners < mu ? sRowRange[oid + j * kOwners] : 0u;
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) ztv[j] = row_first4(sRowEnt, rng[j], sA, sRHS);
+#pragma unroll
+            for (int j = 0; j < RPT; ++j)
+                if ((rng[j] & 0xFFu) > 4u) ztv[j] = row_rest4(sRowEnt, rng[j], sA, sRHS, ztv[j]);
             ROWS_LOOP(j, i) {
-                const double zt = row_dot4(sRowEnt, sRowRange[i], sA, sRHS);
+                const double zt = ztv[j];
                 const unsigned t = (ctype >> (2 * j)) & 3u;
                 const double zr = st.alpha * zt + (1.0 - st.alpha) * z[j];
                 const double zn = fmin(fmax(zr + RINV_OF(t) * y[j], sLo[i]), sHi[i]);

@@ -45,7 +45,7 @@ class Info(C.Structure):
         ("flops_per_factor", C.c_int64), ("smem_bytes_per_factor", C.c_int64),
         ("flops_per_scaling", C.c_int64), ("smem_bytes_per_scaling", C.c_int64),
         ("flops_per_check", C.c_int64), ("smem_bytes_per_check", C.c_int64),
-        ("phase_cycles", C.c_double * 8), ("assemble_cycles", C.c_double),
+        ("phase_cycles", C.c_double * 8), ("chain_cycles", C.c_double), ("assemble_cycles", C.c_double),
     ]
 
 

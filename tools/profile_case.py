@@ -26,6 +26,7 @@ if sum(ph) > 0:
     names = ['load', 'scale', 'factor', 'rhs', 'solve', 'update', 'info', 'store']
     tot = sum(ph)
     its = out['iters'].sum() * repeats
+    print('chain cycles per iteration (warp 0): %.0f' % (info['chain_cycles'] / its))
     print('assemble share of factor: %.1f%%' % (100 * info['assemble_cycles'] / max(ph[2], 1)))
     print('phase cycles (sum over QPs and repeats):', {n: f'{v / tot * 100:.1f}%' for n, v in zip(names, ph)})
     print('per ADMM iteration: ' + ', '.join(f'{n} {ph[k] / its:.0f}' for k, n in enumerate(names) if n in ('rhs', 'solve', 'update')),
