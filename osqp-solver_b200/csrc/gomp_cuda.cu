@@ -24,7 +24,9 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -320,8 +322,19 @@ int load_data(gomp_batch *h, const double *A_val, const double *l, const double 
     if (cold && (!A_val || !l || !u)) return fail(GOMP_ERR_INVALID_ARGUMENT, "setup needs A_val, l and u");
     // bounds validation (OSQP validate_data / osqp_update_bounds: l <= u) on host inputs
     if (l && u && !is_device_pointer(l) && !is_device_pointer(u)) {
-        for (size_t k = 0; k < B * (size_t)s.m; ++k)
-            if (l[k] > u[k]) return fail(GOMP_ERR_INVALID_ARGUMENT, "lower bound exceeds upper bound");
+        const size_t total = B * (size_t)s.m;
+        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, std::thread::hardware_concurrency()), total / 65536 + 1));
+        std::atomic<int> bad{0};
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; ++t)
+            pool.emplace_back([&, t]() {
+                const size_t a = total * t / nt, b = total * (t + 1) / nt;
+                int any = 0;
+                for (size_t k = a; k < b; ++k) any |= (l[k] > u[k]);
+                if (any) bad.store(1);
+            });
+        for (auto &th : pool) th.join();
+        if (bad.load()) return fail(GOMP_ERR_INVALID_ARGUMENT, "lower bound exceeds upper bound");
     }
     CUDA_TRY(cudaEventRecord(h->evc0, h->stream));
     int rc;
