@@ -360,20 +360,31 @@ template <int BS>
 __device__ __forceinline__ double chain_sweep(uint32_t dinv0, uint32_t rhs0, uint32_t off0, uint32_t vb0, int t0, int count, int dir,
                                               int tbo, int nblk, uint32_t blk_bytes, bool fwd, double prev, int lane, int g0, int g1,
                                               uint32_t o0, uint32_t o1, bool has0, bool has1) {
+    // Two lanes per block row: lane = r + 16*half; half 0 multiplies columns [0, CH), half 1 columns [CH, NB);
+    // CH is even so both halves start 16-byte aligned.  Halves the loads and FMAs each lane issues per step.
     constexpr int NB = BS > 0 ? BS : 2;
-    const int rl = lane < NB ? lane : NB - 1;
-    const bool act = lane < NB;
+    constexpr int CH = ((NB / 2) + 1) & ~1;              // 8 for NB = 14
+    constexpr int NC = CH > NB - CH ? CH : NB - CH;       // columns a lane handles at most
+    const int r = lane & 15, half = lane >> 4;
+    const int rl = r < NB ? r : NB - 1;
+    const bool act = half == 0 && r < NB;                 // the lane that owns row r's scalar work
+    const int c0 = half ? CH : 0, nc = half ? NB - CH : CH;
     int t = t0;
 #pragma unroll 1
     for (int it = 0; it < count; ++it, t += dir) {
-        // ---- independent of the previous stage: row of the inverted pivot block, rhs entry, off-diagonal values
-        const uint32_t arow = dinv0 + (uint32_t)((t * NB + rl) * NB) * 8u;
-        double m[NB];
+        // ---- independent of the previous stage
+        const uint32_t arow = dinv0 + (uint32_t)((t * NB + rl) * NB + c0) * 8u;
+        double m[NC];
 #pragma unroll
-        for (int c = 0; c < NB; c += 2) {
-            const double2 d = lds_f64x2(arow + (uint32_t)c * 8u);
-            m[c] = d.x;
-            m[c + 1] = d.y;
+        for (int c = 0; c < NC; c += 2) {
+            if (c < nc) {
+                const double2 d = lds_f64x2(arow + (uint32_t)c * 8u);
+                m[c] = d.x;
+                m[c + 1] = d.y;
+            } else {
+                m[c] = 0.0;
+                m[c + 1] = 0.0;
+            }
         }
         const uint32_t ab = rhs0 + (uint32_t)(t * NB + rl) * 8u;
         const double b = lds_f64(ab);
@@ -382,29 +393,25 @@ __device__ __forceinline__ double chain_sweep(uint32_t dinv0, uint32_t rhs0, uin
         const uint32_t ao = off0 + (uint32_t)(blk ? tb : 0) * blk_bytes;
         const double ov0 = (blk && has0) ? lds_f64(ao + o0) : 0.0;
         const double ov1 = (blk && has1) ? lds_f64(ao + o1) : 0.0;
-        // ---- dependent chain
+        // ---- dependent chain (prev[r] is held by both lanes of row r; sources are lanes < 16)
         const double up0 = __shfl_sync(0xffffffffu, prev, g0);
         const double up1 = __shfl_sync(0xffffffffu, prev, g1);
         const double off = fma(ov0, up0, ov1 * up1);
         const double v = fwd ? b - off : off;
         const uint32_t avb = vb0 + (uint32_t)(t & 1) * 128u;
-        if (act) sts_f64(avb + (uint32_t)lane * 8u, v);
+        if (act) sts_f64(avb + (uint32_t)r * 8u, v);
         __syncwarp();
-        double2 w[NB / 2]; // all broadcast loads in flight before the first FMA
+        double2 w[NC / 2];
 #pragma unroll
-        for (int c = 0; c < NB; c += 2) w[c / 2] = lds_f64x2(avb + (uint32_t)c * 8u);
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int c = 0; c < NC; c += 2) w[c / 2] = c < nc ? lds_f64x2(avb + (uint32_t)(c0 + c) * 8u) : make_double2(0.0, 0.0);
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int c = 0; c < NB; c += 2) {
-            if ((c >> 1) & 1) {
-                a2 = fma(m[c], w[c / 2].x, a2);
-                a3 = fma(m[c + 1], w[c / 2].y, a3);
-            } else {
-                a0 = fma(m[c], w[c / 2].x, a0);
-                a1 = fma(m[c + 1], w[c / 2].y, a1);
-            }
+        for (int c = 0; c < NC; c += 2) {
+            a0 = fma(m[c], w[c / 2].x, a0);
+            a1 = fma(m[c + 1], w[c / 2].y, a1);
         }
-        const double acc = (a0 + a1) + (a2 + a3);
+        double acc = a0 + a1;
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
         prev = fwd ? acc : b - acc;
         if (act) sts_f64(ab, prev);
     }
@@ -670,9 +677,9 @@ static __device__ __noinline__ void solver_role(const DevSym &S, double sigma, u
         }
         // block-tridiagonal solve, in place on sRHS
         const long long t_chain0 = clock64();
-        if (BS > 0 && S.uniform_off && S.ow <= 2 && S.owT <= 2) {
+        if (BS > 0 && BS <= 16 && S.uniform_off && S.ow <= 2 && S.owT <= 2) {
             // ---- fast path (uniform off-diagonal pattern): register-carried stage results, explicit LDS/STS
-            const int rl = lane < bs ? lane : bs - 1;
+            const int rl = (lane & 15) < bs ? (lane & 15) : bs - 1; // two lanes per block row (lane = row + 16*half)
             OffPattern pat;
             load_off_pattern(C, 0, rl, pat);
             const uint32_t dinv0 = C.sm + (uint32_t)C.oDinv, rhs0 = C.sm + (uint32_t)C.oRHS, off0 = C.sm + (uint32_t)C.oOff,
@@ -701,7 +708,8 @@ static __device__ __noinline__ void solver_role(const DevSym &S, double sigma, u
                 if (lane < bs) sRHS[h * bs + lane] = xm;
                 named_bar_sync(2, 64);
                 if (prof != nullptr && tid == 0) atomicAdd(&prof[12], (unsigned long long)(clock64() - t_chain0));
-                chain_sweep<BS>(dinv0, rhs0, off0, vb0, h - 1, h, -1, 0, T - 1, blk_bytes, false, xm, lane, tg0, tg1, to0, to1, th0, th1);
+                const double xm2 = sRHS[h * bs + rl]; // both lanes of a row hold the middle stage's value
+                chain_sweep<BS>(dinv0, rhs0, off0, vb0, h - 1, h, -1, 0, T - 1, blk_bytes, false, xm2, lane, tg0, tg1, to0, to1, th0, th1);
             } else { // stages T-1 .. h+1 forward (Off_t' u_{t+1}), then back down (Off_{t-1} x_{t-1})
                 chain_sweep<BS>(dinv0, rhs0, off0, vb0, T - 1, T - 1 - h, -1, 0, T - 1, blk_bytes, true, 0.0, lane, tg0, tg1, to0, to1, th0, th1);
                 __syncwarp();
