@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "gomp_kernel.cuh"
+#include "gomp_stream.h"
 #include "symbolic.h"
 
 using namespace gomp_dev;
@@ -162,6 +163,9 @@ struct gomp_batch {
     DevBatch db;
     DevSettings dst;
     KernelChoice kernel;
+    bool streamed = false; // long-horizon back end (gomp_stream.cu): QP and factor in a global workspace
+    DevStream dx;
+    DevArray<double> d_ws;
     int device = 0, num_sms = 0, ctas_per_sm = 0, grid = 0;
     size_t smem_bytes = 0, workspace_bytes = 0;
     cudaStream_t stream = nullptr;
@@ -457,7 +461,7 @@ int gomp_batch_destroy(gomp_batch *h) {
     h->d_A.release(); h->d_l.release(); h->d_u.release(); h->d_q.release(); h->d_x0.release(); h->d_xs.release();
     h->d_zs.release(); h->d_ys.release(); h->d_rho.release(); h->d_E.release(); h->d_D.release(); h->d_qs.release(); h->d_dx.release(); h->d_Lg.release(); h->d_Ug.release(); h->d_tri_rc.release(); h->d_dy.release(); h->d_xo.release();
     h->d_yo.release(); h->d_pri.release(); h->d_dua.release(); h->d_obj.release();
-    h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
+    h->d_ws.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evc0) cudaEventDestroy(h->evc0);
@@ -480,8 +484,10 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     else gomp_settings_default(&st);
     if (st.check_termination < 0 || st.max_iter <= 0 || st.scaling < 0 || st.rho <= 0 || st.sigma <= 0 || st.alpha <= 0 || st.alpha >= 2)
         return fail(GOMP_ERR_INVALID_ARGUMENT, "invalid OSQP settings");
-    if (st.linsys == GOMP_LINSYS_PCG || st.linsys == GOMP_LINSYS_BLOCKTRI_GLOBAL)
-        return fail(GOMP_ERR_UNSUPPORTED, "only the shared-memory block-tridiagonal back end is built in this version");
+    if (st.linsys == GOMP_LINSYS_PCG)
+        return fail(GOMP_ERR_UNSUPPORTED, "the PCG back end is not built: long horizons use the exact streamed block-tridiagonal "
+                                          "factorisation (GOMP_LINSYS_BLOCKTRI_GLOBAL), which keeps OSQP's iteration counts");
+    if (st.linsys < GOMP_LINSYS_AUTO || st.linsys > GOMP_LINSYS_PCG) return fail(GOMP_ERR_INVALID_ARGUMENT, "unknown linsys");
 
     gomp_batch *h = new gomp_batch();
     h->st = st;
@@ -518,15 +524,54 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     if ((rc = upload_pattern(h))) return bail(rc);
 
     h->kernel = pick_kernel(h->sym.m_used, h->sym.n_pad, h->sym.bs);
-    if (!h->kernel.launch)
-        return bail(fail(GOMP_ERR_UNSUPPORTED, "problem too large for the register-resident kernel (non-empty rows <= 3584, variables <= 1792)"));
-    if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
-        return bail(fail(GOMP_ERR_UNSUPPORTED, "QP does not fit in shared memory (" + std::to_string(h->smem_bytes) + " bytes needed)"));
+    const bool resident_ok = h->kernel.launch && h->smem_bytes <= (size_t)prop.sharedMemPerBlockOptin;
+    h->streamed = st.linsys == GOMP_LINSYS_BLOCKTRI_GLOBAL || (st.linsys == GOMP_LINSYS_AUTO && !resident_ok);
     int occ = 0;
-    {
+    if (!h->streamed) {
+        if (!h->kernel.launch)
+            return bail(fail(GOMP_ERR_UNSUPPORTED, "problem too large for the register-resident kernel (non-empty rows <= 3584, variables <= 1792)"));
+        if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
+            return bail(fail(GOMP_ERR_UNSUPPORTED, "QP does not fit in shared memory (" + std::to_string(h->smem_bytes) + " bytes needed)"));
         cudaError_t e = h->kernel.prepare(h->smem_bytes, &occ);
         if (e != cudaSuccess) return bail(fail(GOMP_ERR_CUDA, std::string("kernel preparation failed: ") + cudaGetErrorString(e)));
         if (occ < 1) return bail(fail(GOMP_ERR_CUDA, "kernel cannot be resident (occupancy 0)"));
+    } else {
+        // long-horizon back end: x~ in shared memory, everything else in a per-CTA global workspace
+        const gomp::Symbolic &s = h->sym;
+        DevStream &x = h->dx;
+        if (s.bs % 2 != 0 || s.bs > 32)
+            return bail(fail(GOMP_ERR_UNSUPPORTED, "streamed back end needs an even block size <= 32 (16-byte bulk copies)"));
+        size_t o = 0;
+        auto take = [&o](size_t bytes) {
+            size_t at = o;
+            o += (bytes + 15) & ~(size_t)15;
+            return (int)at;
+        };
+        x.slot_doubles = s.bs * s.bs + s.bs * s.ow;
+        x.oRHS = take(8 * (size_t)s.n_pad);
+        x.oRing = take(8 * (size_t)2 * kStreamRing * x.slot_doubles);
+        x.oPub = take(8 * 256);
+        x.oV = take(8 * 128);
+        x.oRed = take(8 * (size_t)kRedK * (kStreamThreads / 32));
+        x.oBar = take(8 * 2 * kStreamRing + 16);
+        h->smem_bytes = o;
+        if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
+            return bail(fail(GOMP_ERR_UNSUPPORTED, "right-hand side of the block solve does not fit in shared memory (" +
+                                                       std::to_string(h->smem_bytes) + " bytes needed)"));
+        cudaError_t e = prepare_stream(h->smem_bytes, &occ);
+        if (e != cudaSuccess) return bail(fail(GOMP_ERR_CUDA, std::string("kernel preparation failed: ") + cudaGetErrorString(e)));
+        if (occ < 1) return bail(fail(GOMP_ERR_CUDA, "kernel cannot be resident (occupancy 0)"));
+        long long w = 0;
+        auto wtake = [&w](long long cnt) {
+            long long at = w;
+            w += (cnt + 1) & ~1LL;
+            return at;
+        };
+        const long long mu1 = std::max(1, s.m_used);
+        x.wA = wtake(s.nnzA); x.wP = wtake(std::max<long long>(1, s.nnzPu)); x.wW = wtake(mu1); x.wRho = wtake(mu1);
+        x.wDinv = wtake((long long)s.T * s.bs * s.bs); x.wOff = wtake(std::max<long long>(1, (long long)std::max(0, s.T - 1) * s.bs * s.ow));
+        x.wT = wtake(s.n_pad); x.wLo = wtake(mu1); x.wHi = wtake(mu1);
+        x.stride = w;
     }
     h->ctas_per_sm = occ;
     h->grid = (int)std::min<int64_t>(batch, (int64_t)h->num_sms * occ);
@@ -546,7 +591,10 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     ALLOC(d_E, B * mu);
     ALLOC(d_D, B * np);
     ALLOC(d_dx, B * np);
-    if (!h->ds.bounds_in_smem) {
+    if (h->streamed) {
+        ALLOC(d_ws, (size_t)h->grid * (size_t)h->dx.stride);
+        h->dx.ws = h->d_ws.p;
+    } else if (!h->ds.bounds_in_smem) {
         ALLOC(d_Lg, B * mu);
         ALLOC(d_Ug, B * mu);
     }
@@ -625,7 +673,8 @@ int gomp_batch_solve(gomp_batch *h) {
     b.pri_res = h->d_pri.p; b.dua_res = h->d_dua.p; b.obj_val = h->d_obj.p; b.work_counter = h->d_counter.p; b.prof = h->d_prof.p;
     CUDA_TRY(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    CUDA_TRY(h->kernel.launch(h->ds, h->db, h->dst, h->grid, h->smem_bytes, h->stream));
+    if (h->streamed) CUDA_TRY(launch_stream(h->ds, h->db, h->dst, h->dx, h->grid, h->smem_bytes, h->stream));
+    else CUDA_TRY(h->kernel.launch(h->ds, h->db, h->dst, h->grid, h->smem_bytes, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     h->launches++;
     h->pending_flags = 0;
@@ -706,7 +755,7 @@ int gomp_batch_info(gomp_batch *h, gomp_info *info) {
     const gomp::Symbolic &s = h->sym;
     info->batch = h->batch; info->n = s.n; info->m = s.m; info->m_used = s.m_used; info->nnzA = s.nnzA; info->nnzP = s.nnzPu;
     info->block_size = s.bs; info->num_blocks = s.T; info->offdiag_width = s.ow;
-    info->linsys = GOMP_LINSYS_BLOCKTRI_SMEM; info->threads_per_cta = kThreads; info->ctas_per_sm = h->ctas_per_sm;
+    info->linsys = h->streamed ? GOMP_LINSYS_BLOCKTRI_GLOBAL : GOMP_LINSYS_BLOCKTRI_SMEM; info->threads_per_cta = h->streamed ? kStreamThreads : kThreads; info->ctas_per_sm = h->ctas_per_sm;
     info->num_sms = h->num_sms; info->grid = h->grid; info->smem_bytes = (int64_t)h->smem_bytes;
     info->workspace_bytes = (int64_t)h->workspace_bytes; info->kernel_launches = h->launches;
     float ms = 0;

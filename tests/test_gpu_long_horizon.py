@@ -1,0 +1,168 @@
+"""Long-horizon back end (GOMP_LINSYS_BLOCKTRI_GLOBAL, osqp-solver_b200/csrc/gomp_stream.cu) through the C ABI
+against the CPU oracle: BASELINE.json configs[3] (H = 400, batch 1 and small batches) and, forced onto
+problems the resident kernel also solves, against the same oracle answers.  Same bar as
+test_gpu_parity.py: equal status / iteration count / rho updates, x and y within 1e-6 relative.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from common import oracle, package
+from test_gpu_parity import REL_TOL, compare, make_solver, oracle_batch, random_qp
+
+pytestmark = pytest.mark.gpu
+
+GLOBAL = 2  # GOMP_LINSYS_BLOCKTRI_GLOBAL
+
+
+def test_streamed_backend_on_resident_shape():
+    """configs[1] shape forced onto the streamed back end: same answers as the oracle, incl. infeasible
+    and multi-check problems."""
+    pkg, O = package(), oracle()
+    pat = pkg.problem.Pattern(pkg.problem.default_config())
+    d = pkg.problem.generate(pat, 0, 320)
+    s = make_solver(pkg, pat, d, settings=pkg.solver.default_settings(linsys=GLOBAL))
+    assert s.info()["linsys"] == GLOBAL
+    s.set_warm_start(d["x0"])
+    got = s.solve(want_y=True)
+    ref = oracle_batch(O, pat, d)
+    compare(got, ref)
+    assert (ref["exit_code"] != 0).any() and (ref["iters"] > 25).any() and (ref["rho_updates"] > 0).any()
+    s.close()
+
+
+@pytest.mark.parametrize("batch", [1, 6])
+def test_long_horizon_400(batch):
+    """configs[3]: N = 7, H = 400 (n = 5600, m = 22372, nnz(A) = 30730); AUTO picks the streamed back end."""
+    pkg, O = package(), oracle()
+    pat = pkg.problem.Pattern(pkg.problem.default_config(waypoints=400))
+    assert (pat.n, pat.m, pat.nnzA) == (5600, 22372, 30730)
+    d = pkg.problem.generate(pat, 40, batch)
+    s = make_solver(pkg, pat, d)
+    info = s.info()
+    assert info["linsys"] == GLOBAL and info["num_blocks"] == 400 and info["block_size"] == 14
+    s.set_warm_start(d["x0"])
+    got = s.solve(want_y=True)
+    ref = oracle_batch(O, pat, d)
+    compare(got, ref)
+    s.close()
+
+
+def test_long_horizon_tight_tolerance():
+    """H = 200, eps 1e-8: many iterations, several rho updates (refactorisations of the streamed factor)."""
+    pkg, O = package(), oracle()
+    pat = pkg.problem.Pattern(pkg.problem.default_config(waypoints=200))
+    d = pkg.problem.generate(pat, 7, 4)
+    s = make_solver(pkg, pat, d, settings=pkg.solver.default_settings(eps_abs=1e-8, eps_rel=1e-8))
+    assert s.info()["linsys"] == GLOBAL
+    s.set_warm_start(d["x0"])
+    got = s.solve(want_y=True)
+    ref = oracle_batch(O, pat, d, settings=O.default_settings(eps_abs=1e-8, eps_rel=1e-8))
+    compare(got, ref)
+    assert (ref["iters"] > 50).any()
+    s.close()
+
+
+def test_long_horizon_sqp_updates():
+    """configs[2] sequence on a long horizon: solve -> relinearise -> update(A, l, u) -> solve, 3 rounds."""
+    pkg, O = package(), oracle()
+    pat = pkg.problem.Pattern(pkg.problem.default_config(waypoints=160))
+    B = 3
+    d = pkg.problem.generate(pat, 500, B)
+    s = make_solver(pkg, pat, d)
+    assert s.info()["linsys"] == GLOBAL
+    s.set_warm_start(d["x0"])
+    Ps = pat.P_scipy()
+    refs = [O.Solver(Ps, pat.A_scipy(d["A_val"][b]), d["l"][b], d["u"][b]) for b in range(B)]
+    for b in range(B):
+        refs[b].warm_start_x(d["x0"][b])
+    for rnd in range(3):
+        got = s.solve(want_y=True)
+        for b in range(B):
+            refs[b].solve()
+        ref = dict(x=np.array([r.x for r in refs]), y=np.array([r.y for r in refs]),
+                   exit_code=np.array([r.exit_code for r in refs]), iters=np.array([r.iter for r in refs]),
+                   rho_updates=np.array([r.rho_updates for r in refs]))
+        compare(got, ref)
+        xs = np.where(np.isnan(ref["x"]), d["x0"], ref["x"])
+        upd = pkg.problem.relinearize(pat, 500, xs)
+        s.update(upd["A_val"], upd["l"], upd["u"])
+        for b in range(B):
+            refs[b].update(upd["A_val"][b], upd["l"][b], upd["u"][b])
+    s.close()
+
+
+@pytest.mark.parametrize("waypoints", [4, 5, 9])
+def test_streamed_short_horizons(waypoints):
+    """Both chains one or two stages long."""
+    pkg, O = package(), oracle()
+    pat = pkg.problem.Pattern(pkg.problem.default_config(waypoints=waypoints))
+    d = pkg.problem.generate(pat, 0, 8)
+    s = make_solver(pkg, pat, d, settings=pkg.solver.default_settings(linsys=GLOBAL))
+    s.set_warm_start(d["x0"])
+    got = s.solve(want_y=True)
+    compare(got, oracle_batch(O, pat, d))
+    s.close()
+
+
+@pytest.mark.parametrize("blocks", [2, 3])
+def test_streamed_two_and_three_blocks(blocks):
+    """T = 2 (bottom chain empty) and T = 3 (both chains a single stage) on a hand-made chain QP:
+    P = tridiag(-1, 2, -1), A = [first differences; identity], block size 4."""
+    pkg, O = package(), oracle()
+    rng = np.random.default_rng(5 + blocks)
+    bs, B = 4, 5
+    n = bs * blocks
+    P = sp.csc_matrix(np.triu(2 * np.eye(n) - np.eye(n, k=1) - np.eye(n, k=-1)))
+    Dm = (np.eye(n, k=1) - np.eye(n))[: n - 1]
+    A = sp.csc_matrix(np.vstack([Dm, np.eye(n)]))
+    A.sort_indices()
+    m = A.shape[0]
+    Ax = np.stack([A.data * (1 + 0.2 * rng.random(A.nnz)) for _ in range(B)])
+    l = np.concatenate([-0.3 * np.ones((B, n - 1)), -1 + 0.5 * rng.random((B, n))], axis=1)
+    u = np.concatenate([0.3 * np.ones((B, n - 1)), 1 + 0.5 * rng.random((B, n))], axis=1)
+    l[:, n - 1] = u[:, n - 1] = 0.4   # x_0 pinned
+    q = rng.standard_normal((B, n))
+    st = pkg.solver.default_settings(eps_abs=1e-7, eps_rel=1e-7, linsys=GLOBAL)
+    s = pkg.solver.BatchQPSolver(n, m, P.indptr, P.indices, P.data, A.indptr, A.indices, Ax, l, u, q=q, settings=st,
+                                 var_order=np.arange(n), block_size=bs)
+    assert s.info()["num_blocks"] == blocks
+    got = s.solve(want_y=True)
+    s.close()
+    ost = O.default_settings(eps_abs=1e-7, eps_rel=1e-7)
+    for b in range(B):
+        Ab = sp.csc_matrix((Ax[b], A.indices, A.indptr), shape=(m, n))
+        r = O.Solver(P, Ab, l[b], u[b], q=q[b], settings=ost)
+        r.solve()
+        assert got["exit_code"][b] == r.exit_code and got["iters"][b] == r.iter
+        assert np.abs(got["x"][b] - r.x).max() < REL_TOL * max(1.0, np.abs(r.x).max())
+        assert np.abs(got["y"][b] - r.y).max() < REL_TOL * max(1.0, np.abs(r.y).max())
+
+
+def test_streamed_general_qp_with_linear_term():
+    """One dense block (T = 1), q != 0, loose / equality / one-sided rows, on the streamed back end."""
+    pkg, O = package(), oracle()
+    rng = np.random.default_rng(11)
+    n, m, B = 12, 18, 6
+    P, A = random_qp(rng, n, m)
+    A.sort_indices()
+    Ax = np.stack([A.data * (1 + 0.1 * rng.standard_normal(A.nnz)) for _ in range(B)])
+    l = -rng.random((B, m)) - 0.1
+    u = rng.random((B, m)) + 0.1
+    l[:, 3] = u[:, 3] = 0.05
+    l[:, 5], u[:, 5] = -1e30, 1e30
+    u[:, 7] = 1e30
+    q = rng.standard_normal((B, n))
+    st = pkg.solver.default_settings(eps_abs=1e-7, eps_rel=1e-7, linsys=GLOBAL)
+    s = pkg.solver.BatchQPSolver(n, m, P.indptr, P.indices, P.data, A.indptr, A.indices, Ax, l, u, q=q, settings=st,
+                                 var_order=np.arange(n), block_size=n)
+    got = s.solve(want_y=True)
+    s.close()
+    ost = O.default_settings(eps_abs=1e-7, eps_rel=1e-7)
+    for b in range(B):
+        Ab = sp.csc_matrix((Ax[b], A.indices, A.indptr), shape=(m, n))
+        r = O.Solver(P, Ab, l[b], u[b], q=q[b], settings=ost)
+        r.solve()
+        assert got["exit_code"][b] == r.exit_code and got["iters"][b] == r.iter
+        assert np.abs(got["x"][b] - r.x).max() < REL_TOL * max(1.0, np.abs(r.x).max())
+        assert np.abs(got["y"][b] - r.y).max() < REL_TOL * max(1.0, np.abs(r.y).max())
