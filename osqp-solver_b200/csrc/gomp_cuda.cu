@@ -166,6 +166,8 @@ struct gomp_batch {
     bool streamed = false; // long-horizon back end (gomp_stream.cu): QP and factor in a global workspace
     DevStream dx;
     DevArray<double> d_ws;
+    DevArray<uint32_t> d_row_ell;
+    DevArray<uint16_t> d_col_ell;
     int device = 0, num_sms = 0, ctas_per_sm = 0, grid = 0;
     size_t smem_bytes = 0, workspace_bytes = 0;
     cudaStream_t stream = nullptr;
@@ -461,7 +463,7 @@ int gomp_batch_destroy(gomp_batch *h) {
     h->d_A.release(); h->d_l.release(); h->d_u.release(); h->d_q.release(); h->d_x0.release(); h->d_xs.release();
     h->d_zs.release(); h->d_ys.release(); h->d_rho.release(); h->d_E.release(); h->d_D.release(); h->d_qs.release(); h->d_dx.release(); h->d_Lg.release(); h->d_Ug.release(); h->d_tri_rc.release(); h->d_dy.release(); h->d_xo.release();
     h->d_yo.release(); h->d_pri.release(); h->d_dua.release(); h->d_obj.release();
-    h->d_ws.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
+    h->d_ws.release(); h->d_row_ell.release(); h->d_col_ell.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evc0) cudaEventDestroy(h->evc0);
@@ -549,8 +551,11 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
         };
         x.slot_doubles = s.bs * s.bs + s.bs * s.ow;
         x.oRHS = take(8 * (size_t)s.n_pad);
-        x.oRing = take(8 * (size_t)2 * kStreamRing * x.slot_doubles);
+        x.ring_doubles = std::max(kStreamRing, kStreamGroup * kStreamGroupRing) * x.slot_doubles;
+        x.oRing = take(8 * (size_t)2 * x.ring_doubles);
         x.oPub = take(8 * 256);
+        x.oDprev = take(8 * (size_t)2 * s.bs * s.bs);
+        x.oOffBuf = take(8 * (size_t)2 * s.bs * std::max(1, s.ow));
         x.oV = take(8 * 128);
         x.oRed = take(8 * (size_t)kRedK * (kStreamThreads / 32));
         x.oBar = take(8 * 2 * kStreamRing + 16);
@@ -558,7 +563,7 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
         if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
             return bail(fail(GOMP_ERR_UNSUPPORTED, "right-hand side of the block solve does not fit in shared memory (" +
                                                        std::to_string(h->smem_bytes) + " bytes needed)"));
-        cudaError_t e = prepare_stream(h->smem_bytes, &occ);
+        cudaError_t e = prepare_stream(s.bs, h->smem_bytes, &occ);
         if (e != cudaSuccess) return bail(fail(GOMP_ERR_CUDA, std::string("kernel preparation failed: ") + cudaGetErrorString(e)));
         if (occ < 1) return bail(fail(GOMP_ERR_CUDA, "kernel cannot be resident (occupancy 0)"));
         long long w = 0;
@@ -572,6 +577,9 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
         x.wDinv = wtake((long long)s.T * s.bs * s.bs); x.wOff = wtake(std::max<long long>(1, (long long)std::max(0, s.T - 1) * s.bs * s.ow));
         x.wT = wtake(s.n_pad); x.wLo = wtake(mu1); x.wHi = wtake(mu1);
         x.stride = w;
+        if (h->d_row_ell.upload(s.row_ent) != cudaSuccess || h->d_col_ell.upload(s.col_row) != cudaSuccess)
+            return bail(fail(GOMP_ERR_ALLOC, "cudaMalloc failed for the ELL pattern views"));
+        x.row_ell = h->d_row_ell.p; x.col_ell = h->d_col_ell.p; x.roww = s.roww; x.colw = s.colw;
     }
     h->ctas_per_sm = occ;
     h->grid = (int)std::min<int64_t>(batch, (int64_t)h->num_sms * occ);
@@ -771,7 +779,7 @@ int gomp_batch_info(gomp_batch *h, gomp_info *info) {
             info->assemble_cycles = (double)pc[8];
             info->chain_cycles = (double)pc[9];
             if (std::getenv("GOMP_PROFILE_PHASES")[0] == '2')
-                std::fprintf(stderr, "chain marks (cumulative cycles): fwd %.0f, after bar1 %.0f, after middle+bar2 %.0f, total %.0f\n", (double)pc[10], (double)pc[11], (double)pc[12], (double)pc[9]);
+                std::fprintf(stderr, "chain marks (cycles): [10] %.0f  [11] %.0f  [12] %.0f  total %.0f\n", (double)pc[10], (double)pc[11], (double)pc[12], (double)pc[9]);
     }
     info->last_solve_ms = h->last_solve_ms;
     info->last_h2d_ms = h->last_h2d_ms;

@@ -105,12 +105,102 @@ __device__ __forceinline__ double pf_dot_g(const DevSym &S, int p, const double 
     return acc;
 }
 
+// ---- the same products on the ELL views, two rows / columns per call ------------------------------------------
+// The entry addresses of an ELL row do not depend on a range word, and two rows are interleaved, so a thread
+// has up to 8 independent L2 loads in flight per level instead of one (these loops are L2-latency bound).
+// Summation order per row / column is the CSR / CSC order, i.e. the results equal the *_g versions bit for bit.
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+#define ELL_ROW2(i1, i2, ...)                                                               \
+    _Pragma("unroll 4") for (int j__ = 0; j__ < X.roww; ++j__) {                            \
+        const uint32_t e1 = __ldg(X.row_ell + (size_t)j__ * mu + (i1));                     \
+        const uint32_t e2 = __ldg(X.row_ell + (size_t)j__ * mu + (i2));                     \
+        const bool h1 = e1 != kNone, h2 = e2 != kNone;                                      \
+        const uint32_t k1 = h1 ? (e1 & 0xFFFFu) : 0u, k2 = h2 ? (e2 & 0xFFFFu) : 0u;         \
+        const uint32_t q1 = h1 ? (e1 >> 16) : 0u, q2 = h2 ? (e2 >> 16) : 0u;                 \
+        __VA_ARGS__                                                                         \
+    }
+__device__ __forceinline__ void row_dot_ell2(const DevStream &X, int mu, int i1, int i2, const double *A, const double *vec, double &r1,
+                                             double &r2) {
+    double a1 = 0.0, a2 = 0.0;
+    ELL_ROW2(i1, i2, {
+        const double v1 = A[k1], v2 = A[k2], w1 = vec[q1], w2 = vec[q2];
+        a1 = h1 ? fma(v1, w1, a1) : a1;
+        a2 = h2 ? fma(v2, w2, a2) : a2;
+    })
+    r1 = a1;
+    r2 = a2;
+}
+__device__ __forceinline__ void row_absmax_ell2(const DevStream &X, int mu, int i1, int i2, const double *A, double &r1, double &r2) {
+    double a1 = 0.0, a2 = 0.0;
+    ELL_ROW2(i1, i2, {
+        const double v1 = A[k1], v2 = A[k2];
+        a1 = h1 ? fmax(a1, fabs(v1)) : a1;
+        a2 = h2 ? fmax(a2, fabs(v2)) : a2;
+        (void)q1; (void)q2;
+    })
+    r1 = a1;
+    r2 = a2;
+}
+__device__ __forceinline__ void row_scale_ell2(const DevStream &X, int mu, int i1, int i2, bool two, double *A, double s1, double s2) {
+    ELL_ROW2(i1, i2, {
+        const double v1 = A[k1], v2 = A[k2];
+        if (h1) A[k1] = v1 * s1;
+        if (h2 && two) A[k2] = v2 * s2;
+        (void)q1; (void)q2;
+    })
+}
+// columns: values are the contiguous CSC range of the column, their compact rows come from the ELL view
+#define ELL_COL2(p1, p2, ...)                                                               \
+    const uint32_t rg1 = __ldg(S.col_range + (p1)), rg2 = __ldg(S.col_range + (p2));       \
+    const int s1__ = (int)(rg1 >> 8), n1__ = (int)(rg1 & 0xFFu), s2__ = (int)(rg2 >> 8), n2__ = (int)(rg2 & 0xFFu); \
+    _Pragma("unroll 4") for (int j__ = 0; j__ < X.colw; ++j__) {                            \
+        const bool h1 = j__ < n1__, h2 = j__ < n2__;                                        \
+        const int k1 = h1 ? s1__ + j__ : 0, k2 = h2 ? s2__ + j__ : 0;                        \
+        __VA_ARGS__                                                                         \
+    }
+__device__ __forceinline__ void col_dot_ell2(const DevSym &S, const DevStream &X, int np, int p1, int p2, const double *A, const double *vec,
+                                             double &r1, double &r2) {
+    double a1 = r1, a2 = r2;
+    ELL_COL2(p1, p2, {
+        const int q1 = __ldg(X.col_ell + (size_t)j__ * np + p1), q2 = __ldg(X.col_ell + (size_t)j__ * np + p2);
+        const double v1 = A[k1], v2 = A[k2], w1 = vec[h1 ? q1 : 0], w2 = vec[h2 ? q2 : 0];
+        a1 = h1 ? fma(v1, w1, a1) : a1;
+        a2 = h2 ? fma(v2, w2, a2) : a2;
+    })
+    r1 = a1;
+    r2 = a2;
+}
+__device__ __forceinline__ void col_absmax2(const DevSym &S, const DevStream &X, int p1, int p2, const double *A, double &r1, double &r2) {
+    double a1 = 0.0, a2 = 0.0;
+    ELL_COL2(p1, p2, {
+        const double v1 = A[k1], v2 = A[k2];
+        a1 = h1 ? fmax(a1, fabs(v1)) : a1;
+        a2 = h2 ? fmax(a2, fabs(v2)) : a2;
+    })
+    r1 = a1;
+    r2 = a2;
+}
+__device__ __forceinline__ void col_scale2(const DevSym &S, const DevStream &X, int p1, int p2, bool two, double *A, double s1, double s2) {
+    ELL_COL2(p1, p2, {
+        const double v1 = A[k1], v2 = A[k2];
+        if (h1) A[k1] = v1 * s1;
+        if (h2 && two) A[k2] = v2 * s2;
+    })
+}
+// pairs of the strided loops: (i, i2) with i2 = i + kST, clamped to i when it falls off the end
+#define ROWS2(i, i2, two) for (int i = tid, i2 = (tid + kST < mu ? tid + kST : tid); i < mu; i += 2 * kST, i2 = (i + kST < mu ? i + kST : i)) if (const bool two = i + kST < mu; true)
+#define COLS2(p, p2, two) for (int p = tid, p2 = (tid + kST < np ? tid + kST : tid); p < np; p += 2 * kST, p2 = (p + kST < np ? p + kST : p)) if (const bool two = p + kST < np; true)
+
 // ---- factorisation: one pivot block, by one 224-thread group, entries in registers --------------------------
 // mode bit 1: subtract Off_{t-1} Dinv_{t-1} Off_{t-1}' first; bit 2: subtract Off_t' Dinv_{t+1} Off_t.
-__device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dall, const double *Offall, double *pub, int t, int mode,
-                                                    int g, int gl) {
-    constexpr int EPL = 5; // ceil(32 * 32 / 224)
-    const int bs = S.bs, nn = bs * bs;
+// `dprev` (shared memory, bs*bs doubles per group) carries the inverse of the previous stage of the chain to the
+// next call, so the Schur update never waits on the global copy just written.
+// `offbuf` (shared memory, bs*ow doubles per group) stages the off-diagonal block of the Schur update.
+template <int BS>
+__device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dall, const double *Offall, double *pub, double *dprev,
+                                                    double *offbuf, bool prev_valid, int t, int mode, int g, int gl) {
+    constexpr int EPL = BS > 0 ? (BS * BS + kGroup - 1) / kGroup : 5; // entries per thread (bs <= 32)
+    const int bs = BS > 0 ? BS : S.bs, nn = bs * bs;
     double *M = Dall + (size_t)t * nn;
     double val[EPL];
     int ri[EPL], ci[EPL];
@@ -126,8 +216,13 @@ __device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dal
         if (!(mode & pass)) continue;
         const bool above = pass == 1;
         const int tb = above ? t - 1 : t;
-        const double *Dn = Dall + (size_t)(above ? t - 1 : t + 1) * nn;
-        const double *blk = Offall + (size_t)tb * bs * S.ow;
+        const double *Dn = prev_valid ? dprev : Dall + (size_t)(above ? t - 1 : t + 1) * nn;
+        const double *gblk = Offall + (size_t)tb * bs * S.ow;
+        if (pass == 2 && (mode & 1)) named_bar_sync(4 + g, kGroup); // middle stage: the first pass is done with offbuf
+        for (int e = gl; e < bs * S.ow; e += kGroup) offbuf[e] = gblk[e];
+        named_bar_sync(4 + g, kGroup);
+        const double *blk = offbuf;
+        const int tp = S.uniform_off ? 0 : tb; // pattern block (L1-resident when every block shares one pattern)
         const int cnt = above ? S.ow : S.owT;
 #pragma unroll
         for (int q = 0; q < EPL; ++q) {
@@ -138,22 +233,22 @@ __device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dal
                 int a;
                 double va = 0.0;
                 if (above) {
-                    a = __ldg(S.off_col + (tb * bs + r) * S.ow + s1);
+                    a = __ldg(S.off_col + (tp * bs + r) * S.ow + s1);
                     if (a >= 0) va = blk[r * S.ow + s1];
                 } else {
-                    a = __ldg(S.offT_row + (tb * bs + r) * S.owT + s1);
-                    if (a >= 0) va = blk[__ldg(S.offT_slot + (tb * bs + r) * S.owT + s1)];
+                    a = __ldg(S.offT_row + (tp * bs + r) * S.owT + s1);
+                    if (a >= 0) va = blk[__ldg(S.offT_slot + (tp * bs + r) * S.owT + s1)];
                 }
                 if (a < 0) continue;
                 for (int s2 = 0; s2 < cnt; ++s2) {
                     int b2;
                     double vb = 0.0;
                     if (above) {
-                        b2 = __ldg(S.off_col + (tb * bs + c) * S.ow + s2);
+                        b2 = __ldg(S.off_col + (tp * bs + c) * S.ow + s2);
                         if (b2 >= 0) vb = blk[c * S.ow + s2];
                     } else {
-                        b2 = __ldg(S.offT_row + (tb * bs + c) * S.owT + s2);
-                        if (b2 >= 0) vb = blk[__ldg(S.offT_slot + (tb * bs + c) * S.owT + s2)];
+                        b2 = __ldg(S.offT_row + (tp * bs + c) * S.owT + s2);
+                        if (b2 >= 0) vb = blk[__ldg(S.offT_slot + (tp * bs + c) * S.owT + s2)];
                     }
                     if (b2 >= 0) acc += va * Dn[a * bs + b2] * vb;
                 }
@@ -181,9 +276,13 @@ __device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dal
             else val[q] = pinv;
         }
     }
+    named_bar_sync(4 + g, kGroup); // every thread is done reading dprev (Schur update) and the last pivot row / column
 #pragma unroll
     for (int q = 0; q < EPL; ++q)
-        if (ri[q] >= 0) M[gl + q * kGroup] = val[q];
+        if (ri[q] >= 0) {
+            M[gl + q * kGroup] = val[q];
+            dprev[gl + q * kGroup] = val[q];
+        }
     named_bar_sync(4 + g, kGroup); // the next stage of this chain reads the inverse just stored
 }
 
@@ -208,17 +307,30 @@ __device__ __forceinline__ Step step_of(int warp, int j, int T, int h) {
     return s;
 }
 
+#define SMARK(ph)                                                                   \
+    do {                                                                            \
+        if (B.prof != nullptr && tid == 0) {                                        \
+            const long long now__ = clock64();                                      \
+            atomicAdd(&B.prof[ph], (unsigned long long)(now__ - t_phase));          \
+            t_phase = now__;                                                        \
+        }                                                                           \
+    } while (0)
+
 } // namespace
 
+template <int BS>
 __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_constant__ DevSym S, const __grid_constant__ DevBatch B,
                                                                   const __grid_constant__ DevSettings st,
                                                                   const __grid_constant__ DevStream X) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bs = S.bs, T = S.T, np = S.n_pad, mu = S.m_used, h = S.T / 2, bb = bs * bs;
+    const int bs = BS > 0 ? BS : S.bs;
+    const int T = S.T, np = S.n_pad, mu = S.m_used, h = S.T / 2, bb = bs * bs;
     double *const sRHS = reinterpret_cast<double *>(smem_raw + X.oRHS);
     double *const sRing = reinterpret_cast<double *>(smem_raw + X.oRing);
     double *const sPub = reinterpret_cast<double *>(smem_raw + X.oPub);
+    double *const sDprev = reinterpret_cast<double *>(smem_raw + X.oDprev); // [2][bs*bs]
+    double *const sOffBuf = reinterpret_cast<double *>(smem_raw + X.oOffBuf); // [2][bs*ow]
     double *const sV = reinterpret_cast<double *>(smem_raw + X.oV);
     double *const sRed = reinterpret_cast<double *>(smem_raw + X.oRed);
     uint64_t *const sFull = reinterpret_cast<uint64_t *>(smem_raw + X.oBar); // [2][kRing]
@@ -236,11 +348,20 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
     __syncthreads();
 
     const int slotD = X.slot_doubles;
-    const int halves = bs <= 16 ? 2 : 1;
+    const int halves = bs <= 16 ? 2 : 1; // two lanes per block row when the block has at most 16 rows
     const int rr_ = halves == 2 ? (lane & 15) : lane, half = halves == 2 ? (lane >> 4) : 0;
     const bool rowact = rr_ < bs;
     const int r = rowact ? rr_ : bs - 1;
     const int cchunk = (bs + halves - 1) / halves, c0 = half * cchunk, c1 = min(bs, c0 + cchunk);
+    // uniform off-diagonal pattern (every GOMP horizon): this lane's row / column pattern, loaded once
+    const bool upat = S.uniform_off && S.ow <= kMaxW && S.owT <= kMaxW;
+    int ua[kMaxW], ub[kMaxW], us[kMaxW];
+#pragma unroll
+    for (int q = 0; q < kMaxW; ++q) {
+        ua[q] = (upat && q < S.ow) ? S.off_col[r * S.ow + q] : -1;
+        ub[q] = (upat && q < S.owT) ? S.offT_row[r * S.owT + q] : -1;
+        us[q] = (upat && q < S.owT) ? S.offT_slot[r * S.owT + q] : 0;
+    }
 
     for (;;) {
         if (tid == 0) *sWork = atomicAdd(B.work_counter, 1);
@@ -253,6 +374,7 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
         double *const gx = B.x_state + bnp, *const gz = B.z_state + bmu, *const gy = B.y_state + bmu;
         double *const gE = B.Eg + bmu, *const gD = B.Dg + bnp, *const gdy = B.dyg + bmu, *const gdx = B.dxg + bnp;
         double *const gq = hasq ? B.qs + bnp : nullptr;
+        long long t_phase = clock64();
 
         // ------------------------------------------------------------------ load
         {
@@ -279,44 +401,55 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
         }
         block_max<1>(bad, sRed, tid); // (also: the loads above are visible to every thread)
         const bool empty_infeasible = bad[0] != 0.0;
+        SMARK(PH_LOAD);
 
         // ------------------------------------------------------------------ Ruiz equilibration
         double cscale = 1.0;
 #pragma unroll 1
         for (int it = 0; it < st.scaling; ++it) {
-            for (int p = tid; p < np; p += kST) {
-                const double nrm = fmax(pf_absmax_g(S, p, gP), col_absmax_g(S, p, gA));
-                gT[p] = 1.0 / sqrt(limit_scaling(nrm));
+            COLS2(p, p2, two) {
+                double na, nb;
+                col_absmax2(S, X, p, p2, gA, na, nb);
+                const double pa = pf_absmax_g(S, p, gP), pb = pf_absmax_g(S, p2, gP);
+                gT[p] = 1.0 / sqrt(limit_scaling(fmax(pa, na)));
+                if (two) gT[p2] = 1.0 / sqrt(limit_scaling(fmax(pb, nb)));
             }
-            for (int i = tid; i < mu; i += kST) {
-                const uint32_t rg = __ldg(S.row_range + i);
-                double nrm = 0.0;
-                for (int q = (int)(rg >> 8), q1 = q + (int)(rg & 0xFFu); q < q1; ++q) nrm = fmax(nrm, fabs(gA[__ldg(S.row_csr + q) & 0xFFFFu]));
-                gW[i] = 1.0 / sqrt(limit_scaling(nrm));
+            ROWS2(i, i2, two) {
+                double na, nb;
+                row_absmax_ell2(X, mu, i, i2, gA, na, nb);
+                gW[i] = 1.0 / sqrt(limit_scaling(na));
+                if (two) gW[i2] = 1.0 / sqrt(limit_scaling(nb));
             }
             __syncthreads();
-            for (int i = tid; i < mu; i += kST) {
-                const uint32_t rg = __ldg(S.row_range + i);
-                const double et = gW[i];
-                for (int q = (int)(rg >> 8), q1 = q + (int)(rg & 0xFFu); q < q1; ++q) gA[__ldg(S.row_csr + q) & 0xFFFFu] *= et;
-                gE[i] *= et;
+            ROWS2(i, i2, two) {
+                const double ea = gW[i], eb = gW[i2];
+                row_scale_ell2(X, mu, i, i2, two, gA, ea, eb);
+                gE[i] *= ea;
+                if (two) gE[i2] *= eb;
             }
+#pragma unroll 4
             for (int k = tid; k < S.nnzPu; k += kST) {
                 const uint32_t ij = __ldg(S.Pu_ij + k);
                 gP[k] = (gP[k] * gT[ij >> 16]) * gT[ij & 0xFFFFu];
             }
             __syncthreads();
             double psum = 0.0, qn[1] = {0.0};
-            for (int p = tid; p < np; p += kST) {
-                const double dt = gT[p];
-                const uint32_t rg = __ldg(S.col_range + p);
-                for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) gA[k] *= dt;
-                gD[p] *= dt;
+            COLS2(p, p2, two) {
+                const double da = gT[p], db = gT[p2];
+                col_scale2(S, X, p, p2, two, gA, da, db);
+                gD[p] *= da;
+                if (two) gD[p2] *= db;
                 if (hasq) {
-                    gq[p] *= dt;
+                    gq[p] *= da;
                     qn[0] = fmax(qn[0], fabs(gq[p]));
+                    if (two) {
+                        gq[p2] *= db;
+                        qn[0] = fmax(qn[0], fabs(gq[p2]));
+                    }
                 }
-                psum += pf_absmax_g(S, p, gP);
+                const double pa = pf_absmax_g(S, p, gP), pb = pf_absmax_g(S, p2, gP);
+                psum += pa;
+                if (two) psum += pb;
             }
             psum = block_sum(psum, sRed, tid);
             block_max<1>(qn, sRed, tid);
@@ -334,6 +467,7 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
         }
         const double cinv = 1.0 / cscale;
         const bool uns = !st.scaled_termination;
+        SMARK(PH_SCALE);
 
         // ------------------------------------------------------------------ iterates
         const int flags = B.flag_bits;
@@ -354,14 +488,19 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                 gx[p] = var >= 0 ? (1.0 / gD[p]) * B.x0[(size_t)b * S.n + var] : 0.0;
             }
             __syncthreads();
-            for (int i = tid; i < mu; i += kST) gz[i] = row_dot_g(S, i, gA, gx);
+            ROWS2(i, i2, two) {
+                double za, zb;
+                row_dot_ell2(X, mu, i, i2, gA, gx, za, zb);
+                gz[i] = za;
+                if (two) gz[i2] = zb;
+            }
         }
         __syncthreads();
 
         int status = empty_infeasible ? -3 : -10;
         int iters_done = 0;
         double pri_res = 0.0, dua_res = 0.0;
-        bool need_factor = true;
+        bool need_factor = true, w_dirty = true;
 
 #pragma unroll 1
         for (int iter = 1; status == -10 && iter <= st.max_iter; ++iter) {
@@ -407,117 +546,74 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                     }
                 }
                 __syncthreads();
+                SMARK(PH_ASSEMBLE);
                 if (tid < 2 * kGroup) {
                     const int g = tid / kGroup, gl_ = tid - g * kGroup;
-                    double *pub = sPub + g * 128;
+                    double *pub = sPub + g * 128, *dprev = sDprev + (size_t)g * bb, *obuf = sOffBuf + (size_t)g * bs * S.ow;
                     if (g == 0) {
 #pragma unroll 1
-                        for (int t = 0; t < h; ++t) factor_block_stream(S, gDinv, gOff, pub, t, t > 0 ? 1 : 0, 0, gl_);
+                        for (int t = 0; t < h; ++t) factor_block_stream<BS>(S, gDinv, gOff, pub, dprev, obuf, true, t, t > 0 ? 1 : 0, 0, gl_);
                     } else {
 #pragma unroll 1
-                        for (int t = T - 1; t > h; --t) factor_block_stream(S, gDinv, gOff, pub, t, t < T - 1 ? 2 : 0, 1, gl_);
+                        for (int t = T - 1; t > h; --t) factor_block_stream<BS>(S, gDinv, gOff, pub, dprev, obuf, true, t, t < T - 1 ? 2 : 0, 1, gl_);
                     }
                 }
                 __syncthreads();
-                if (tid < kGroup) factor_block_stream(S, gDinv, gOff, sPub, h, (h > 0 ? 1 : 0) | (h < T - 1 ? 2 : 0), 0, tid);
+                // the middle stage takes both neighbours' inverses from the global copies
+                if (tid < kGroup) factor_block_stream<BS>(S, gDinv, gOff, sPub, sDprev, sOffBuf, false, h, (h > 0 ? 1 : 0) | (h < T - 1 ? 2 : 0), 0, tid);
                 fence_proxy_async_all(); // the factor is read by bulk copies (async proxy) from here on
                 __syncthreads();
                 need_factor = false;
+                w_dirty = true;
+                SMARK(PH_FACTOR);
             }
             // ---------------- rhs = sigma x - q + A'(rho z - y)
-            for (int i = tid; i < mu; i += kST) gW[i] = fma(gRho[i], gz[i], -gy[i]);
-            __syncthreads();
-            for (int p = tid; p < np; p += kST) {
-                double acc = st.sigma * gx[p];
-                if (hasq) acc -= gq[p];
-                sRHS[p] = col_dot_g(S, p, gA, gW, acc);
+            if (w_dirty) {
+#pragma unroll 4
+                for (int i = tid; i < mu; i += kST) gW[i] = fma(gRho[i], gz[i], -gy[i]);
+                __syncthreads();
+                w_dirty = false;
+            }
+            COLS2(p, p2, two) {
+                double ra = st.sigma * gx[p], rb = st.sigma * gx[p2];
+                if (hasq) {
+                    ra -= gq[p];
+                    rb -= gq[p2];
+                }
+                col_dot_ell2(S, X, np, p, p2, gA, gW, ra, rb);
+                sRHS[p] = ra;
+                if (two) sRHS[p2] = rb;
             }
             __syncthreads();
+            SMARK(PH_RHS);
 
             // ---------------- block-tridiagonal solve in place on sRHS (warps 0 and 1)
             if (warp < 2) {
-                const int nsteps = warp == 0 ? 2 * h + 1 : 2 * (T - 1 - h);
                 const bool two_chains = T - 1 - h > 0; // T <= 2: the bottom chain is empty, warp 1 has nothing to wait for
-                double *ring = sRing + (size_t)warp * kStreamRing * slotD;
+                double *ring = sRing + (size_t)warp * X.ring_doubles;
                 uint64_t *full = sFull + warp * kStreamRing;
                 double *vb = sV + warp * 64;
-                auto issue = [&](int j) { // lane 0: start the bulk copies of step j
-                    const Step sp = step_of(warp, j, T, h);
-                    const uint32_t slot = (ring_k + (uint32_t)j) % kStreamRing;
-                    double *dst = ring + (size_t)slot * slotD;
-                    const uint32_t bytesD = (uint32_t)bb * 8u, bytesO = (uint32_t)(bs * S.ow) * 8u;
-                    const bool has_off = sp.ob >= 0 && sp.ob < T - 1;
-                    mbar_expect_tx(full + slot, bytesD + (has_off ? bytesO : 0u));
-                    bulk_g2s(dst, gDinv + (size_t)sp.t * bb, bytesD, full + slot);
-                    if (has_off) bulk_g2s(dst + bb, gOff + (size_t)sp.ob * bs * S.ow, bytesO, full + slot);
-                };
-                if (lane == 0) {
-                    fence_proxy_async();
-                    for (int j = 0; j < kStreamRing - 1 && j < nsteps; ++j) issue(j);
-                }
-#pragma unroll 1
-                for (int j = 0; j < nsteps; ++j) {
-                    const Step sp = step_of(warp, j, T, h);
-                    if (warp == 0 && j == h && two_chains) named_bar_sync(1, 64); // middle stage: needs the bottom chain's forward sweep
-                    if (warp == 1 && j == T - 1 - h) {
-                        named_bar_sync(1, 64);
-                        named_bar_sync(2, 64);                          // ... and the bottom chain's way back needs x_h
-                    }
-                    // the slot consumed one step ago is free: refill it kRing-1 steps ahead
-                    if (lane == 0 && j + kStreamRing - 1 < nsteps) {
-                        fence_proxy_async();
-                        issue(j + kStreamRing - 1);
-                    }
-                    // off-diagonal pattern of this step (does not depend on the chain)
-                    const bool from_above = sp.kind == 0 || sp.kind == 2 || sp.kind == 4;
-                    const bool from_below = sp.kind == 1 || sp.kind == 2 || sp.kind == 3;
+                // one substitution step in plain C++ (generic pattern / block size; also the middle stage of the fast path)
+                auto substep = [&](const Step sp, const double *Dm, const double *Oa, const double *Ot, double *vbj) {
+                    const bool from_above = (sp.kind == 0 || sp.kind == 2 || sp.kind == 4) && sp.t > 0;
+                    const bool from_below = (sp.kind == 1 || sp.kind == 2 || sp.kind == 3) && sp.t < T - 1;
                     const bool fwd = sp.kind <= 2;
-                    int ia[kMaxW], ib[kMaxW], sb[kMaxW];
-#pragma unroll
-                    for (int s = 0; s < kMaxW; ++s) {
-                        ia[s] = -1;
-                        ib[s] = -1;
-                        sb[s] = 0;
-                        if (from_above && sp.t > 0 && s < S.ow) ia[s] = __ldg(S.off_col + ((size_t)(sp.t - 1) * bs + r) * S.ow + s);
-                        if (from_below && sp.t < T - 1 && s < S.owT) {
-                            ib[s] = __ldg(S.offT_row + ((size_t)sp.t * bs + r) * S.owT + s);
-                            sb[s] = __ldg(S.offT_slot + ((size_t)sp.t * bs + r) * S.owT + s);
-                        }
-                    }
-                    const uint32_t kk = ring_k + (uint32_t)j, slot = kk % kStreamRing, parity = (kk / kStreamRing) & 1u;
-                    {
-                        unsigned spins = 0;
-                        while (!mbar_try_wait(full + slot, parity)) {
-                            if (++spins > (1u << 26)) __trap();
-                        }
-                    }
-                    const double *Dm = ring + (size_t)slot * slotD, *Ob = Dm + bb;
                     double a = fwd ? sRHS[sp.t * bs + r] : 0.0;
-                    if (from_above && sp.t > 0) {
-                        // rows of stage t against the stage above: Off_{t-1}[r][s] * v_{t-1}[col]
-                        const double *Oa = Ob; // streamed block is Off_{t-1} for kinds 0, 2, 4
+                    if (from_above) { // rows of stage t against the stage above: Off_{t-1}[r][s] * v_{t-1}[col]
                         const double *src = sRHS + (sp.t - 1) * bs;
-#pragma unroll
-                        for (int s = 0; s < kMaxW; ++s)
-                            if (ia[s] >= 0) a = fma(-Oa[r * S.ow + s], src[ia[s]], a);
-                        for (int s = kMaxW; s < S.ow; ++s) {
-                            const int cidx = __ldg(S.off_col + ((size_t)(sp.t - 1) * bs + r) * S.ow + s);
+                        for (int s = 0; s < S.ow; ++s) {
+                            const int cidx = upat ? S.off_col[r * S.ow + s] : __ldg(S.off_col + ((size_t)(sp.t - 1) * bs + r) * S.ow + s);
                             if (cidx >= 0) a = fma(-Oa[r * S.ow + s], src[cidx], a);
                         }
                     }
-                    if (from_below && sp.t < T - 1) {
-                        // columns of Off_t against the stage below: Off_t[row][slot]' * v_{t+1}[row]
-                        const double *Ot = sp.kind == 2 ? gOff + (size_t)sp.t * bs * S.ow : Ob; // the middle stage streams Off_{h-1}
+                    if (from_below) { // columns of Off_t against the stage below: Off_t[row][slot]' * v_{t+1}[row]
                         const double *src = sRHS + (sp.t + 1) * bs;
-#pragma unroll
-                        for (int s = 0; s < kMaxW; ++s)
-                            if (ib[s] >= 0) a = fma(-Ot[sb[s]], src[ib[s]], a);
-                        for (int s = kMaxW; s < S.owT; ++s) {
-                            const int ridx = __ldg(S.offT_row + ((size_t)sp.t * bs + r) * S.owT + s);
-                            if (ridx >= 0) a = fma(-Ot[__ldg(S.offT_slot + ((size_t)sp.t * bs + r) * S.owT + s)], src[ridx], a);
+                        for (int s = 0; s < S.owT; ++s) {
+                            const size_t at = (upat ? (size_t)r : (size_t)sp.t * bs + r) * S.owT + s;
+                            const int ridx = __ldg(S.offT_row + at);
+                            if (ridx >= 0) a = fma(-Ot[__ldg(S.offT_slot + at)], src[ridx], a);
                         }
                     }
-                    double *vbj = vb + (j & 1) * 32;
                     if (half == 0 && rowact) vbj[r] = a;
                     __syncwarp();
                     double acc = 0.0;
@@ -525,11 +621,137 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                     if (halves == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
                     if (half == 0 && rowact) sRHS[sp.t * bs + r] = fwd ? acc : sRHS[sp.t * bs + r] + acc;
                     __syncwarp();
-                    if (warp == 0 && j == h && two_chains) named_bar_sync(2, 64); // x_h published for the bottom chain
+                };
+                auto wait_slot = [&](uint32_t slot, uint32_t parity) {
+                    unsigned spins = 0;
+                    while (!mbar_try_wait(full + slot, parity)) {
+                        if (++spins > (1u << 26)) __trap(); // a lost bulk copy must not hang the device
+                    }
+                };
+                // the middle stage needs the forward sweeps of both chains; its result starts both ways back
+                auto middle = [&]() {
+                    if (warp == 0) {
+                        if (two_chains) named_bar_sync(1, 64);
+                        Step sp;
+                        sp.t = h; sp.ob = h - 1; sp.kind = 2;
+                        substep(sp, gDinv + (size_t)h * bb, gOff + (size_t)max(h - 1, 0) * bs * S.ow, gOff + (size_t)h * bs * S.ow, vb);
+                        if (two_chains) named_bar_sync(2, 64);
+                    } else if (two_chains) {
+                        named_bar_sync(1, 64);
+                        named_bar_sync(2, 64);
+                    }
+                };
+                const bool fast = BS > 0 && BS <= 16 && upat && S.ow <= 2 && S.owT <= 2;
+                if (fast) {
+                    // ---- fast path: the factor streams in groups of kStreamGroup stages (one bulk copy for the
+                    // pivot-block inverses, one for the off-diagonal blocks); inside a group the hand-scheduled
+                    // sweep of the resident kernel runs on the slot as if it were the resident factor
+                    const int L = warp == 0 ? h : T - 1 - h; // stages of this chain
+                    const int ng = (L + kStreamGroup - 1) / kStreamGroup, ngroups = 2 * ng;
+                    const int blkD = bs * S.ow, grpD = kStreamGroup * (bb + blkD);
+                    struct Grp { int t0, cnt, dir, tbo; bool fwd; };
+                    auto group_of = [&](int gi) {
+                        Grp g;
+                        const bool first = gi < ng;
+                        const int k = first ? gi : gi - ng;
+                        g.cnt = min(kStreamGroup, L - k * kStreamGroup);
+                        g.fwd = first;
+                        if (warp == 0) {
+                            if (first) { g.t0 = k * kStreamGroup; g.dir = 1; g.tbo = -1; }
+                            else { g.t0 = h - 1 - k * kStreamGroup; g.dir = -1; g.tbo = 0; }
+                        } else {
+                            if (first) { g.t0 = T - 1 - k * kStreamGroup; g.dir = -1; g.tbo = 0; }
+                            else { g.t0 = h + 1 + k * kStreamGroup; g.dir = 1; g.tbo = -1; }
+                        }
+                        return g;
+                    };
+                    auto issue_group = [&](int gi) { // lane 0
+                        const Grp g = group_of(gi);
+                        const int tlo = g.dir > 0 ? g.t0 : g.t0 - g.cnt + 1;
+                        const uint32_t slot = (ring_k + (uint32_t)gi) % kStreamGroupRing;
+                        double *dst = ring + (size_t)slot * grpD;
+                        const int b_lo = max(tlo + g.tbo, 0), b_hi = min(tlo + g.cnt - 1 + g.tbo, T - 2);
+                        const uint32_t bytesD = (uint32_t)(g.cnt * bb) * 8u, bytesO = b_hi >= b_lo ? (uint32_t)((b_hi - b_lo + 1) * blkD) * 8u : 0u;
+                        mbar_expect_tx(full + slot, bytesD + bytesO);
+                        bulk_g2s(dst, gDinv + (size_t)tlo * bb, bytesD, full + slot);
+                        if (bytesO) bulk_g2s(dst + kStreamGroup * bb + (b_lo - (tlo + g.tbo)) * blkD, gOff + (size_t)b_lo * blkD, bytesO, full + slot);
+                    };
+                    if (lane == 0) {
+                        fence_proxy_async();
+                        for (int gi = 0; gi < kStreamGroupRing - 1 && gi < ngroups; ++gi) issue_group(gi);
+                    }
+                    const uint32_t rhs0 = smem_u32(sRHS), vb0 = smem_u32(vb), ring0 = smem_u32(ring);
+                    const uint32_t blk_bytes = (uint32_t)blkD * 8u;
+                    // per-lane pattern constants: forward = row r of the block above, transposed = column r of the block below
+                    const int fg0 = ua[0] >= 0 ? ua[0] : 0, fg1 = ua[1] >= 0 ? ua[1] : 0;
+                    const uint32_t fo0 = (uint32_t)(r * S.ow) * 8u, fo1 = fo0 + 8u;
+                    const bool fh0 = ua[0] >= 0, fh1 = ua[1] >= 0;
+                    const int tg0 = ub[0] >= 0 ? ub[0] : 0, tg1 = ub[1] >= 0 ? ub[1] : 0;
+                    const uint32_t to0 = (uint32_t)us[0] * 8u, to1 = (uint32_t)us[1] * 8u;
+                    const bool th0 = ub[0] >= 0, th1 = ub[1] >= 0;
+                    double prev = 0.0;
+                    if (ng == 0) middle();
+#pragma unroll 1
+                    for (int gi = 0; gi < ngroups; ++gi) {
+                        if (gi == ng) {
+                            middle();
+                            prev = sRHS[h * bs + r];
+                        }
+                        // the slot consumed one group ago is free (its reads retired inside the sweep): refill it
+                        if (lane == 0 && gi + kStreamGroupRing - 1 < ngroups) issue_group(gi + kStreamGroupRing - 1);
+                        const Grp g = group_of(gi);
+                        const uint32_t kk = ring_k + (uint32_t)gi, slot = kk % kStreamGroupRing;
+                        wait_slot(slot, (kk / kStreamGroupRing) & 1u);
+                        const int tlo = g.dir > 0 ? g.t0 : g.t0 - g.cnt + 1;
+                        const uint32_t sl = ring0 + slot * (uint32_t)grpD * 8u;
+                        const uint32_t dinv0 = sl - (uint32_t)(tlo * bb) * 8u;                                    // virtual base: stage t at + t*bb*8
+                        const uint32_t off0 = sl + (uint32_t)(kStreamGroup * bb) * 8u - (uint32_t)(tlo + g.tbo) * blk_bytes; // block tb at + tb*blk_bytes
+                        const bool tr = g.tbo == 0;
+                        prev = chain_sweep<BS>(dinv0, rhs0, off0, vb0, g.t0, g.cnt, g.dir, g.tbo, T - 1, blk_bytes, g.fwd, prev, lane,
+                                               tr ? tg0 : fg0, tr ? tg1 : fg1, tr ? to0 : fo0, tr ? to1 : fo1, tr ? th0 : fh0, tr ? th1 : fh1);
+                    }
+                    ring_k += (uint32_t)ngroups;
+                } else {
+                    // ---- generic path: one ring slot per stage
+                    const int nsteps = warp == 0 ? 2 * h + 1 : 2 * (T - 1 - h);
+                    auto issue = [&](int j) { // lane 0: start the bulk copies of step j
+                        const Step sp = step_of(warp, j, T, h);
+                        const uint32_t slot = (ring_k + (uint32_t)j) % kStreamRing;
+                        double *dst = ring + (size_t)slot * slotD;
+                        const uint32_t bytesD = (uint32_t)bb * 8u, bytesO = (uint32_t)(bs * S.ow) * 8u;
+                        const bool has_off = sp.ob >= 0 && sp.ob < T - 1;
+                        mbar_expect_tx(full + slot, bytesD + (has_off ? bytesO : 0u));
+                        bulk_g2s(dst, gDinv + (size_t)sp.t * bb, bytesD, full + slot);
+                        if (has_off) bulk_g2s(dst + bb, gOff + (size_t)sp.ob * bs * S.ow, bytesO, full + slot);
+                    };
+                    if (lane == 0) {
+                        fence_proxy_async();
+                        for (int j = 0; j < kStreamRing - 1 && j < nsteps; ++j) issue(j);
+                    }
+#pragma unroll 1
+                    for (int j = 0; j < nsteps; ++j) {
+                        const Step sp = step_of(warp, j, T, h);
+                        if (warp == 0 && j == h && two_chains) named_bar_sync(1, 64); // middle stage: needs the bottom chain's forward sweep
+                        if (warp == 1 && j == T - 1 - h) {
+                            named_bar_sync(1, 64);
+                            named_bar_sync(2, 64); // ... and the bottom chain's way back needs x_h
+                        }
+                        // the slot consumed one step ago is free: refill it kStreamRing-1 steps ahead
+                        // (its last generic-proxy reads retired before the previous step's closing __syncwarp)
+                        if (lane == 0 && j + kStreamRing - 1 < nsteps) issue(j + kStreamRing - 1);
+                        const uint32_t kk = ring_k + (uint32_t)j, slot = kk % kStreamRing;
+                        wait_slot(slot, (kk / kStreamRing) & 1u);
+                        const double *Dm = ring + (size_t)slot * slotD, *Ob = Dm + bb;
+                        // kinds 0, 2, 4 stream Off_{t-1}; kinds 1, 3 stream Off_t; the middle stage reads Off_h from L2
+                        substep(sp, Dm, Ob, sp.kind == 2 ? gOff + (size_t)sp.t * bs * S.ow : Ob, vb + (j & 1) * 32);
+                        if (warp == 0 && j == h && two_chains) named_bar_sync(2, 64); // x_h published for the bottom chain
+                    }
+                    ring_k += (uint32_t)nsteps;
                 }
-                ring_k += (uint32_t)nsteps;
             }
+            if (B.prof != nullptr && tid == 0) atomicAdd(&B.prof[PH_CHAIN], (unsigned long long)(clock64() - t_phase));
             __syncthreads();
+            SMARK(PH_SOLVE);
 
             const bool last = iter == st.max_iter;
             const bool can_check = st.check_termination && (iter % st.check_termination == 0);
@@ -542,43 +764,72 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                 if (do_info && hasq) gdx[p] = xn - xo;
                 gx[p] = xn;
             }
-            for (int i = tid; i < mu; i += kST) {
-                const double zt = row_dot_g(S, i, gA, sRHS);
-                const double rv = gRho[i], zo = gz[i], yo_ = gy[i];
-                const double zr = st.alpha * zt + (1.0 - st.alpha) * zo;
-                const double zn = fmin(fmax(zr + (1.0 / rv) * yo_, gLo[i]), gHi[i]);
-                const double d = rv * (zr - zn);
-                gy[i] = yo_ + d;
-                gz[i] = zn;
-                if (do_info) gdy[i] = d;
+            ROWS2(i, i2, two) {
+                double zta, ztb;
+                row_dot_ell2(X, mu, i, i2, gA, sRHS, zta, ztb);
+                const double rva = gRho[i], zoa = gz[i], yoa = gy[i], loa = gLo[i], hia = gHi[i];
+                const double rvb = gRho[i2], zob = gz[i2], yob = gy[i2], lob = gLo[i2], hib = gHi[i2];
+                {
+                    const double zr = st.alpha * zta + (1.0 - st.alpha) * zoa;
+                    const double zn = fmin(fmax(zr + (1.0 / rva) * yoa, loa), hia);
+                    const double d = rva * (zr - zn), yn = yoa + d;
+                    gy[i] = yn;
+                    gz[i] = zn;
+                    gW[i] = fma(rva, zn, -yn); // w = rho z - y for the next gather
+                    if (do_info) gdy[i] = d;
+                }
+                if (two) {
+                    const double zr = st.alpha * ztb + (1.0 - st.alpha) * zob;
+                    const double zn = fmin(fmax(zr + (1.0 / rvb) * yob, lob), hib);
+                    const double d = rvb * (zr - zn), yn = yob + d;
+                    gy[i2] = yn;
+                    gz[i2] = zn;
+                    gW[i2] = fma(rvb, zn, -yn);
+                    if (do_info) gdy[i2] = d;
+                }
             }
             __syncthreads();
+            SMARK(PH_UPDATE);
 
             if (do_info) {
                 // ---------------- residuals and the norms OSQP's tolerances need (update_info)
+                w_dirty = true; // the infeasibility test below borrows gW
                 double pri_u, pri_s, pn_u, pn_s, dua_u, dua_s, dn_u, dn_s;
                 {
                     double na[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                    for (int i = tid; i < mu; i += kST) {
-                        const double ax = row_dot_g(S, i, gA, gx);
-                        const double zi = gz[i];
-                        const double pr = ax - zi;
-                        const double einv = 1.0 / gE[i];
-                        na[0] = fmax(na[0], fabs(einv * pr));
-                        na[1] = fmax(na[1], fabs(pr));
-                        na[2] = fmax(na[2], fabs(einv * zi));
-                        na[3] = fmax(na[3], fabs(einv * ax));
-                        na[4] = fmax(na[4], fabs(zi));
-                        na[5] = fmax(na[5], fabs(ax));
+                    ROWS2(i, i2, two) {
+                        double axa, axb;
+                        row_dot_ell2(X, mu, i, i2, gA, gx, axa, axb);
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+                            if (w == 1 && !two) break;
+                            const int ii = w ? i2 : i;
+                            const double ax = w ? axb : axa;
+                            const double zi = gz[ii];
+                            const double pr = ax - zi;
+                            const double einv = 1.0 / gE[ii];
+                            na[0] = fmax(na[0], fabs(einv * pr));
+                            na[1] = fmax(na[1], fabs(pr));
+                            na[2] = fmax(na[2], fabs(einv * zi));
+                            na[3] = fmax(na[3], fabs(einv * ax));
+                            na[4] = fmax(na[4], fabs(zi));
+                            na[5] = fmax(na[5], fabs(ax));
+                        }
                     }
                     block_max<6>(na, sRed, tid);
                     pri_u = na[0]; pri_s = na[1]; pn_u = fmax(na[2], na[3]); pn_s = fmax(na[4], na[5]);
                 }
                 {
                     double nb[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                    for (int p = tid; p < np; p += kST) {
+                    COLS2(p0, p2, two) {
+                      double atya = 0.0, atyb = 0.0;
+                      col_dot_ell2(S, X, np, p0, p2, gA, gy, atya, atyb);
+#pragma unroll
+                      for (int w = 0; w < 2; ++w) {
+                        if (w == 1 && !two) break;
+                        const int p = w ? p2 : p0;
                         const double px = pf_dot_g(S, p, gP, gx);
-                        const double aty = col_dot_g(S, p, gA, gy, 0.0);
+                        const double aty = w ? atyb : atya;
                         const double qq = hasq ? gq[p] : 0.0;
                         const double du = qq + px + aty;
                         const double dinv = 1.0 / gD[p];
@@ -590,6 +841,7 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                         nb[5] = fmax(nb[5], fabs(px));
                         nb[6] = fmax(nb[6], fabs(aty));
                         nb[7] = fmax(nb[7], fabs(qq));
+                      }
                     }
                     block_max<8>(nb, sRed, tid);
                     dua_u = nb[0]; dua_s = nb[1]; dn_u = fmax(nb[4], fmax(nb[3], nb[2])); dn_s = fmax(nb[7], fmax(nb[6], nb[5]));
@@ -706,6 +958,7 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                 }
                 if (!done && last) status = -2;
                 __syncthreads();
+                SMARK(PH_INFO);
             }
         }
 
@@ -735,17 +988,20 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
             B.dua_res[b] = dua_res;
         }
         __syncthreads();
+        SMARK(PH_STORE);
     }
 }
 
-cudaError_t prepare_stream(size_t smem_bytes, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(gomp_admm_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+cudaError_t prepare_stream(int bs, size_t smem_bytes, int *ctas_per_sm) {
+    auto fn = bs == 14 ? gomp_admm_stream_kernel<14> : gomp_admm_stream_kernel<0>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, gomp_admm_stream_kernel, kST, smem_bytes);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, fn, kST, smem_bytes);
 }
 cudaError_t launch_stream(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int grid, size_t smem_bytes,
                           cudaStream_t stream) {
-    gomp_admm_stream_kernel<<<grid, kST, smem_bytes, stream>>>(S, B, st, X);
+    if (S.bs == 14) gomp_admm_stream_kernel<14><<<grid, kST, smem_bytes, stream>>>(S, B, st, X);
+    else gomp_admm_stream_kernel<0><<<grid, kST, smem_bytes, stream>>>(S, B, st, X);
     return cudaGetLastError();
 }
 

@@ -7,7 +7,9 @@
 
 namespace gomp_dev {
 
-constexpr int kStreamRing = 8;      // factor slots in flight per substitution warp
+constexpr int kStreamRing = 8;      // generic path: factor slots (one stage each) in flight per substitution warp
+constexpr int kStreamGroup = 8;     // fast path: stages per bulk copy
+constexpr int kStreamGroupRing = 3; // fast path: groups in flight per substitution warp
 constexpr int kStreamThreads = 512; // threads per CTA of the streamed kernel
 
 struct DevStream {
@@ -17,11 +19,15 @@ struct DevStream {
     // rho per row, pivot-block inverses [T][bs][bs], ELL off-diagonal blocks, column scratch, scaled bounds
     long long wA, wP, wW, wRho, wDinv, wOff, wT, wLo, wHi;
     // shared memory (byte offsets)
-    int oRHS, oRing, oPub, oV, oRed, oBar;
+    int oRHS, oRing, oPub, oDprev, oOffBuf, oV, oRed, oBar;
+    const uint32_t *row_ell; // [roww][m_used] (pos << 16 | value index), 0xFFFFFFFF = none
+    const uint16_t *col_ell; // [colw][n_pad] compact row of the j-th entry of a column
+    int roww, colw;
     int slot_doubles; // bs*bs + bs*ow, one ring slot
+    int ring_doubles; // ring size per substitution warp
 };
 
-cudaError_t prepare_stream(size_t smem_bytes, int *ctas_per_sm);
+cudaError_t prepare_stream(int bs, size_t smem_bytes, int *ctas_per_sm);
 cudaError_t launch_stream(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int grid, size_t smem_bytes,
                           cudaStream_t stream);
 
