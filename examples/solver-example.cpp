@@ -14,9 +14,9 @@ constexpr double TIME_STEP = 0.1;
 constexpr size_t DIMS = 6;
 
 int main(int argc, char **argv) {
-    // the reference runs 802 waypoints; that horizon needs the long-horizon back end, so the default here is
-    // the largest horizon the shared-memory kernel takes for 6 joints
-    const size_t WAYPOINTS = argc > 1 ? (size_t)std::atoi(argv[1]) : 60;
+    // the reference's horizon (examples/solver-example.cpp:12): 802 waypoints -> the streamed long-horizon back
+    // end; horizons up to ~60 waypoints run on the shared-memory resident kernel
+    const size_t WAYPOINTS = argc > 1 ? (size_t)std::atoi(argv[1]) : 802;
     const gomp::ArmGeometry geo = gomp::pandaLikeGeometry();
     std::vector<RobotBall> mappers{
         RobotBall([geo](double *q) { double p[3]; gomp::armPoint<DIMS>(geo, q, 4, 0.0, p); return std::tuple<double, double, double>{p[0], p[1], p[2]}; },

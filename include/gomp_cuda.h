@@ -56,10 +56,12 @@ extern "C" {
 #define GOMP_EXIT_UNKNOWN 10
 
 /* linear-system back ends */
-#define GOMP_LINSYS_AUTO 0
-#define GOMP_LINSYS_BLOCKTRI_SMEM 1   /* block-tridiagonal reduced KKT, factor resident in shared memory */
-#define GOMP_LINSYS_BLOCKTRI_GLOBAL 2 /* same factorisation, factor in L2/HBM (long horizons) */
-#define GOMP_LINSYS_PCG 3             /* reduced-KKT preconditioned CG (long horizons) */
+#define GOMP_LINSYS_AUTO 0            /* resident kernel when the QP fits one SM, else the streamed one */
+#define GOMP_LINSYS_BLOCKTRI_SMEM 1   /* block-tridiagonal reduced KKT, QP + factor resident in registers / shared memory */
+#define GOMP_LINSYS_BLOCKTRI_GLOBAL 2 /* same factorisation, QP + factor in an L2-resident workspace, factor streamed
+                                         through shared memory with TMA (long horizons: H = 400, the reference example's 802) */
+#define GOMP_LINSYS_PCG 3             /* reserved: not built (an inexact solve would change OSQP's iteration counts);
+                                         gomp_batch_create returns GOMP_ERR_UNSUPPORTED */
 
 typedef struct gomp_batch gomp_batch;
 
