@@ -301,8 +301,16 @@ def run_gpu(args):
     if os.path.exists(peaks_path):
         hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     ksec = kernel_avg_ms * 1e-3
+    # DRAM bytes of one launch from the committed ncu --set full capture (same kernel, same workload)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * B / tj["qps_per_launch"]
+        traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum per launch, " + tj["capture"]
     roofline = {"bound": "smem", "achieved": smem_bytes / ksec / 1e9, "peak": smem_peak, "unit": "GB/s",
-                "frac": smem_bytes / ksec / 1e9 / smem_peak, "traffic": None,
+                "frac": smem_bytes / ksec / 1e9 / smem_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_hbm_bytes": hbm_bytes,
                 "peak_source": "measured live (gomp_measure_peaks: conflict-free 16-byte shared-memory loads on all SMs)",
                 "kernel": "gomp_admm_kernel", "kernel_ms": kernel_avg_ms,
                 "fp64": {"achieved": flops / ksec / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops / ksec / 1e12 / fp64_peak,
