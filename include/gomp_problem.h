@@ -1,7 +1,8 @@
 /*
  * gomp_problem.h -- C ABI of libgomp_host: synthetic GOMP trajectory QPs for a whole batch.
  *
- * Host-only (no CUDA).  It drives the facade's ConstraintBuilder<N> exactly as the
+ * The generator is host-only (no CUDA); the device-side re-linearisation at the end of this header lives in
+ * libgomp_cuda.  The generator drives the facade's ConstraintBuilder<N> exactly as the
  * reference's GOMPSolver does (reference src/gomp-solver.h:57-64 initConstraints + build,
  * :83-87 withObstacles + build, :105-116 warm start) with the repo's synthetic arm standing
  * in for the un-vendored UR5e kinematics, and hands out what the solver boundary consumes:
@@ -57,6 +58,38 @@ int gomp_problem_check(const gomp_problem_config *cfg, int64_t first_id, int64_t
  * q [count, N] -> xyz [count, 3], jac [count, 3, N] (nullable). */
 int gomp_problem_fk(const gomp_problem_config *cfg, int32_t ball, int64_t count, const double *q, double *xyz,
                     double *jac);
+
+/* ---- inputs of the device-side re-linearisation (host side, libgomp_host) -------------------------------- */
+
+/* Obstacle lines of problems first_id .. first_id+count-1: lines [count, n_obstacles, 5] =
+ * unit direction (x, y), a point of the line (x, y, z); all lines are passed from above. */
+int gomp_problem_scene(const gomp_problem_config *cfg, int64_t first_id, int64_t count, double *lines);
+
+/* Cartesian rows in the order ConstraintBuilder::withObstacles writes them (reference
+ * src/constraints/constraint-builder.h:90-122: ball-major, per waypoint the x/y/z workspace rows of the
+ * gripper ball, then one row per obstacle).  rows [n_rows] = row index in A, kidx [n_rows, N] = position of
+ * each cell (columns w*N .. w*N+N-1) in the CSC value array.  Call with rows = kidx = NULL for n_rows. */
+int gomp_problem_cart_rows(const gomp_problem_config *cfg, int64_t *n_rows, int32_t *rows, int32_t *kidx);
+
+/* ---- device-side withObstacles / isSolutionOK (libgomp_cuda, sm_100a) ------------------------------------------
+ * The SQP round of reference src/gomp-solver.h:83-87 without leaving the GPU: batched forward kinematics +
+ * Jacobian of the synthetic arm, collision classification against the horizontal lines
+ * (src/horizontal-line.h:78-98) and the linearised bounds, written in place into the device arrays the solver
+ * reads (gomp_batch_update with borrow_inputs).  The kinematic model must be known to the device, so this
+ * covers the repo's synthetic arm only; user-supplied FK callbacks stay on the host path. */
+typedef struct gomp_device_scene gomp_device_scene;
+
+int gomp_device_scene_create(gomp_device_scene **out, const gomp_problem_config *cfg, int64_t count, int64_t n, int64_t m,
+                             int64_t nnzA, const double *lines /* host, gomp_problem_scene */, int64_t n_rows,
+                             const int32_t *rows, const int32_t *kidx /* host, gomp_problem_cart_rows */, int32_t device);
+/* x [count, n] (device): trajectories to linearise around; a problem whose x is NaN (infeasible QP) uses its
+ * row of x_fallback (nullable: then that problem is left untouched).  A_val [count, nnzA], l/u [count, m]
+ * (device) are updated in place; only the Cartesian rows are written.  Asynchronous on `stream`. */
+int gomp_device_relinearize(gomp_device_scene *s, const double *x, const double *x_fallback, double *A_val, double *l,
+                            double *u, void *stream);
+/* isSolutionOK (reference src/gomp-solver.h:141-199): ok [count] (device int32) = 1 / 0. */
+int gomp_device_check(gomp_device_scene *s, const double *x, int32_t *ok, void *stream);
+int gomp_device_scene_destroy(gomp_device_scene *s);
 
 #ifdef __cplusplus
 }

@@ -215,6 +215,54 @@ struct Ops {
         });
         return 0;
     }
+    // per-problem obstacle lines for the device-side re-linearisation: [count][O][5] = unit direction (x, y), point (x, y, z)
+    static int scene(const gomp_problem_config &cfg, int64_t first, int64_t count, double *lines) {
+        Scene<N> sc(cfg);
+        parallelFor(count, 0, [&](int64_t i) {
+            Instance<N> in = drawInstance<N>(cfg, sc.geo, first + i);
+            for (int k = 0; k < cfg.n_obstacles; ++k) {
+                double *o = lines + ((size_t)i * cfg.n_obstacles + k) * 5;
+                o[0] = in.lines[k].direction()[0];
+                o[1] = in.lines[k].direction()[1];
+                o[2] = in.lines[k].point()[0];
+                o[3] = in.lines[k].point()[1];
+                o[4] = in.lines[k].point()[2];
+            }
+        });
+        return 0;
+    }
+    // Cartesian rows in the order withObstacles writes them (constraint-builder.h: ball-major, waypoint, [x, y, z box
+    // rows of the gripper], one row per obstacle): row index and CSC value index of each of the N cells
+    static int cartRows(const gomp_problem_config &cfg, int64_t *n_rows, int32_t *rows, int32_t *kidx) {
+        Scene<N> sc(cfg);
+        const int W = cfg.waypoints;
+        int64_t count = 0;
+        for (const RobotBall &b : sc.balls) count += (int64_t)W * ((b.is_gripper ? 3 : 0) + cfg.n_obstacles);
+        if (n_rows) *n_rows = count;
+        if (!rows || !kidx) return 0;
+        int64_t n, m, nnzA;
+        dims(cfg, &n, &m, &nnzA, nullptr);
+        std::vector<int64_t> Ap((size_t)n + 1), Ai((size_t)nnzA);
+        pattern(cfg, Ap.data(), Ai.data(), nullptr, nullptr, nullptr, nullptr);
+        // first Cartesian row: after the dynamics equalities and the N*(W + W-1 + W-2) box rows of q, v, a
+        const int64_t dyn_rows = (int64_t)N * (W - 1);
+        int64_t row = dyn_rows + (int64_t)N * (W + W - 1 + W - 2);
+        int64_t r = 0;
+        for (const RobotBall &b : sc.balls)
+            for (int w = 0; w < W; ++w)
+                for (int k = 0; k < (b.is_gripper ? 3 : 0) + cfg.n_obstacles; ++k, ++row, ++r) {
+                    rows[r] = (int32_t)row;
+                    for (int j = 0; j < N; ++j) {
+                        const int64_t col = (int64_t)w * N + j;
+                        int64_t hit = -1;
+                        for (int64_t q = Ap[(size_t)col]; q < Ap[(size_t)col + 1]; ++q)
+                            if (Ai[(size_t)q] == row) hit = q;
+                        if (hit < 0) return 2; // the builder's row layout changed: refuse rather than scribble
+                        kidx[r * N + j] = (int32_t)hit;
+                    }
+                }
+        return 0;
+    }
     static int fk(const gomp_problem_config &cfg, int32_t ball, int64_t count, const double *q, double *xyz, double *jac) {
         gomp::ArmGeometry g = gomp::pandaLikeGeometry();
         const int upto = ball == 0 ? N : (N >= 5 ? 4 : (N > 1 ? N - 1 : 1));
@@ -290,6 +338,16 @@ int gomp_problem_check(const gomp_problem_config *cfg, int64_t first_id, int64_t
                        int32_t nthreads) {
     if (!valid(cfg) || count < 0 || !x || !ok) return 1;
     DISPATCH(cfg, check(*cfg, first_id, count, x, ok, nthreads));
+}
+
+int gomp_problem_scene(const gomp_problem_config *cfg, int64_t first_id, int64_t count, double *lines) {
+    if (!valid(cfg) || count < 0 || (!lines && cfg->n_obstacles > 0)) return 1;
+    DISPATCH(cfg, scene(*cfg, first_id, count, lines));
+}
+
+int gomp_problem_cart_rows(const gomp_problem_config *cfg, int64_t *n_rows, int32_t *rows, int32_t *kidx) {
+    if (!valid(cfg)) return 1;
+    DISPATCH(cfg, cartRows(*cfg, n_rows, rows, kidx));
 }
 
 int gomp_problem_fk(const gomp_problem_config *cfg, int32_t ball, int64_t count, const double *q, double *xyz,

@@ -135,3 +135,75 @@ def fk(cfg, q, ball=0, want_jac=False):
     if rc:
         raise ValueError("gomp_problem_fk failed")
     return (xyz, jac) if want_jac else xyz
+
+
+def scene(pattern, first_id, count):
+    """Obstacle lines of the problems: [count, n_obstacles, 5] = unit direction (x, y), point (x, y, z)."""
+    cfg = pattern.cfg
+    lines = np.zeros((count, max(cfg.n_obstacles, 1), 5), dtype=np.float64)[:, :cfg.n_obstacles]
+    lines = np.ascontiguousarray(lines)
+    rc = lib().gomp_problem_scene(C.byref(cfg), C.c_int64(first_id), C.c_int64(count), _p(lines) if lines.size else None)
+    if rc:
+        raise ValueError("gomp_problem_scene failed")
+    return lines
+
+
+def cart_rows(pattern):
+    """Cartesian row table in withObstacles order: (rows [R] int32, kidx [R, N] int32)."""
+    cfg = pattern.cfg
+    nr = C.c_int64()
+    if lib().gomp_problem_cart_rows(C.byref(cfg), C.byref(nr), None, None):
+        raise ValueError("gomp_problem_cart_rows failed")
+    rows = np.zeros(nr.value, dtype=np.int32)
+    kidx = np.zeros((nr.value, cfg.n_dim), dtype=np.int32)
+    rc = lib().gomp_problem_cart_rows(C.byref(cfg), C.byref(nr), _p(rows), _p(kidx))
+    if rc:
+        raise ValueError(f"gomp_problem_cart_rows failed ({rc})")
+    return rows, kidx
+
+
+class DeviceScene:
+    """Device-side withObstacles / isSolutionOK (include/gomp_problem.h, implemented in libgomp_cuda):
+    re-linearises the Cartesian rows of A_val / l / u of `count` problems in place, on the GPU.
+    Arguments of relinearize / check are CUDA torch tensors (or raw device pointers as ints)."""
+
+    def __init__(self, pattern, first_id, count, device=-1):
+        from . import solver as _solver
+        self._L = _solver.lib()
+        self.pattern, self.count = pattern, count
+        lines = scene(pattern, first_id, count)
+        rows, kidx = cart_rows(pattern)
+        self.h = C.c_void_p()
+        rc = self._L.gomp_device_scene_create(C.byref(self.h), C.byref(pattern.cfg), C.c_int64(count), C.c_int64(pattern.n),
+                                              C.c_int64(pattern.m), C.c_int64(pattern.nnzA), _p(lines) if lines.size else None,
+                                              C.c_int64(len(rows)), _p(rows), _p(kidx), C.c_int32(device))
+        if rc:
+            raise RuntimeError(f"gomp_device_scene_create failed ({rc}): no CUDA device or table mismatch")
+
+    @staticmethod
+    def _dp(t):
+        if t is None:
+            return None
+        return C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else int(t))
+
+    def relinearize(self, x, A_val, l, u, x_fallback=None, stream=None):
+        rc = self._L.gomp_device_relinearize(self.h, self._dp(x), self._dp(x_fallback), self._dp(A_val), self._dp(l), self._dp(u),
+                                             C.c_void_p(stream or 0))
+        if rc:
+            raise RuntimeError(f"gomp_device_relinearize failed ({rc})")
+
+    def check(self, x, ok, stream=None):
+        rc = self._L.gomp_device_check(self.h, self._dp(x), self._dp(ok), C.c_void_p(stream or 0))
+        if rc:
+            raise RuntimeError(f"gomp_device_check failed ({rc})")
+
+    def close(self):
+        if self.h:
+            self._L.gomp_device_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

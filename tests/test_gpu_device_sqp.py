@@ -1,0 +1,95 @@
+"""Device-side withObstacles / isSolutionOK (osqp-solver_b200/csrc/gomp_relin.cu) against the
+host facade (ConstraintBuilder::withObstacles through libgomp_host), and BASELINE.json configs[2] -- the
+warm-started SQP re-solve sequence -- run without leaving the GPU, checked round by round against the oracle
+fed with the very arrays the device produced."""
+import numpy as np
+import pytest
+
+from common import oracle, package
+from test_gpu_parity import compare, make_solver
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(n_balls=2, n_obstacles=2), dict(n_dim=6, waypoints=12), dict(n_dim=3, waypoints=20, n_obstacles=0)])
+def test_device_relinearize_matches_host(kw):
+    import torch
+    pkg = package()
+    P = pkg.problem
+    pat = P.Pattern(P.default_config(**kw))
+    first, B = 11, 64
+    d = P.generate(pat, first, B)
+    rng = np.random.default_rng(2)
+    x = d["x0"] + 0.05 * rng.standard_normal(d["x0"].shape)
+    x[5] = np.nan                      # an infeasible QP hands back NaN: that problem uses the fallback trajectory
+    xf = np.where(np.isnan(x), d["x0"], x)
+    want = P.relinearize(pat, first, xf)
+    dev = {k: torch.from_numpy(d[k]).cuda() for k in ("A_val", "l", "u", "x0")}
+    sc = P.DeviceScene(pat, first, B)
+    sc.relinearize(torch.from_numpy(x).cuda(), dev["A_val"], dev["l"], dev["u"], x_fallback=dev["x0"])
+    torch.cuda.synchronize()
+    A_val, l, u = (dev[k].cpu().numpy() for k in ("A_val", "l", "u"))
+    # same classification (which rows are active) and the same numbers up to sin/cos rounding
+    assert ((l > -1e29) == (want["l"] > -1e29)).all() and ((u < 1e29) == (want["u"] < 1e29)).all()
+    np.testing.assert_allclose(A_val, want["A_val"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(l, want["l"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(u, want["u"], rtol=1e-13, atol=1e-13)
+    assert (want["l"] != d["l"]).any()
+    # isSolutionOK
+    ok = torch.empty(B, dtype=torch.int32, device="cuda")
+    sc.check(torch.from_numpy(x).cuda(), ok)
+    torch.cuda.synchronize()
+    host_ok = P.check(pat, first, xf)
+    host_ok[5] = False                 # NaN trajectory: not a solution
+    np.testing.assert_array_equal(ok.cpu().numpy().astype(bool), host_ok)
+    sc.close()
+
+
+def test_sqp_sequence_stays_on_device():
+    """configs[2]: solve -> withObstacles(x) -> update(A, l, u) -> solve ... with x, A_val, l, u resident in HBM
+    (borrowed by the solver, rewritten in place by the re-linearisation kernel on the solver's stream)."""
+    import torch
+    pkg, O = package(), oracle()
+    P = pkg.problem
+    pat = P.Pattern(P.default_config())
+    first, B, rounds = 200, 24, 4
+    d = P.generate(pat, first, B)
+    stream = torch.cuda.Stream()
+    dev = {k: torch.from_numpy(d[k]).cuda() for k in ("A_val", "l", "u", "x0")}
+    st = pkg.solver.default_settings(borrow_inputs=1)
+    st.stream = stream.cuda_stream
+    s = make_solver(pkg, pat, dev, settings=st, batch=B)
+    s.set_warm_start(dev["x0"])
+    sc = P.DeviceScene(pat, first, B)
+    xdev = torch.empty((B, pat.n), dtype=torch.float64, device="cuda")
+    ydev = torch.empty((B, pat.m), dtype=torch.float64, device="cuda")
+    ok = torch.empty(B, dtype=torch.int32, device="cuda")
+    Ps = pat.P_scipy()
+    refs = [O.Solver(Ps, pat.A_scipy(d["A_val"][b]), d["l"][b], d["u"][b]) for b in range(B)]
+    for b in range(B):
+        refs[b].warm_start_x(d["x0"][b])
+    seen_active = False
+    for rnd in range(rounds):
+        s.solve_async()
+        got = s.get(x=xdev, y=ydev)
+        got["x"], got["y"] = xdev.cpu().numpy(), ydev.cpu().numpy()
+        for b in range(B):
+            refs[b].solve()
+        ref = dict(x=np.array([r.x for r in refs]), y=np.array([r.y for r in refs]),
+                   exit_code=np.array([r.exit_code for r in refs]), iters=np.array([r.iter for r in refs]),
+                   rho_updates=np.array([r.rho_updates for r in refs]))
+        compare(got, ref)
+        # next round: everything on the device, same stream as the solver
+        sc.check(xdev, ok, stream=stream.cuda_stream)
+        sc.relinearize(xdev, dev["A_val"], dev["l"], dev["u"], x_fallback=dev["x0"], stream=stream.cuda_stream)
+        s.update(dev["A_val"], dev["l"], dev["u"])
+        stream.synchronize()
+        A_val, l, u = (dev[k].cpu().numpy() for k in ("A_val", "l", "u"))
+        seen_active |= bool((l != d["l"]).any())
+        for b in range(B):                      # the oracle gets the arrays the device produced
+            refs[b].update(A_val[b], l[b], u[b])
+        xs = np.where(np.isnan(got["x"]), d["x0"], got["x"])
+        np.testing.assert_array_equal(ok.cpu().numpy().astype(bool) | np.isnan(got["x"][:, 0]), P.check(pat, first, xs) | np.isnan(got["x"][:, 0]))
+    assert seen_active
+    s.close()
+    sc.close()
