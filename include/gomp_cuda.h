@@ -155,6 +155,13 @@ int gomp_batch_get(gomp_batch *h, double *x, double *y, int32_t *exit_code, int3
 int gomp_batch_get_info(gomp_batch *h, double *pri_res, double *dua_res, double *rho,
                         double *obj_val);
 
+/* Per-problem mask for the following solves: active [batch] int32 (host or device; borrowed when it is a
+ * device pointer and settings.borrow_inputs is set), NULL = every problem.  A problem with active == 0 is
+ * skipped: its iterates, rho and last results stay untouched.  This is what a batched SQP loop
+ * (reference src/gomp-solver.h:70-88, one QPSolver per problem there) needs once some problems have
+ * converged or failed while others still iterate. */
+int gomp_batch_set_active(gomp_batch *h, const int32_t *active);
+
 int gomp_batch_info(gomp_batch *h, gomp_info *info);
 int gomp_batch_sync(gomp_batch *h);
 int gomp_batch_destroy(gomp_batch *h);

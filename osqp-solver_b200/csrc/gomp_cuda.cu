@@ -189,7 +189,8 @@ struct gomp_batch {
     // per-batch storage
     DevArray<double> d_A, d_l, d_u, d_q, d_x0, d_xs, d_zs, d_ys, d_rho, d_E, d_D, d_qs, d_dy, d_dx, d_Lg, d_Ug, d_xo, d_yo, d_pri, d_dua, d_obj;
     DevArray<unsigned long long> d_prof;
-    DevArray<int> d_status, d_iters, d_rup, d_counter;
+    DevArray<int> d_status, d_iters, d_rup, d_counter, d_active;
+    const int *active_src = nullptr; // per-QP mask of the next solves (device), NULL = all
     const double *A_src = nullptr, *l_src = nullptr, *u_src = nullptr, *q_src = nullptr; // borrowed device inputs
     long long A_pitch = 0;
     std::vector<int> h_status;
@@ -463,7 +464,7 @@ int gomp_batch_destroy(gomp_batch *h) {
     h->d_A.release(); h->d_l.release(); h->d_u.release(); h->d_q.release(); h->d_x0.release(); h->d_xs.release();
     h->d_zs.release(); h->d_ys.release(); h->d_rho.release(); h->d_E.release(); h->d_D.release(); h->d_qs.release(); h->d_dx.release(); h->d_Lg.release(); h->d_Ug.release(); h->d_tri_rc.release(); h->d_dy.release(); h->d_xo.release();
     h->d_yo.release(); h->d_pri.release(); h->d_dua.release(); h->d_obj.release();
-    h->d_ws.release(); h->d_row_ell.release(); h->d_col_ell.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
+    h->d_active.release(); h->d_ws.release(); h->d_row_ell.release(); h->d_col_ell.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evc0) cudaEventDestroy(h->evc0);
@@ -678,7 +679,7 @@ int gomp_batch_solve(gomp_batch *h) {
     b.x_state = h->d_xs.p; b.z_state = h->d_zs.p; b.y_state = h->d_ys.p; b.rho_state = h->d_rho.p; b.flag_bits = h->pending_flags;
     b.Eg = h->d_E.p; b.Dg = h->d_D.p; b.qs = h->d_qs.p; b.dyg = h->d_dy.p; b.dxg = h->d_dx.p; b.Lg = h->d_Lg.p; b.Ug = h->d_Ug.p; b.x_out = h->d_xo.p; b.y_out = h->d_yo.p;
     b.status = h->d_status.p; b.iters = h->d_iters.p; b.rho_updates = h->d_rup.p;
-    b.pri_res = h->d_pri.p; b.dua_res = h->d_dua.p; b.obj_val = h->d_obj.p; b.work_counter = h->d_counter.p; b.prof = h->d_prof.p;
+    b.pri_res = h->d_pri.p; b.dua_res = h->d_dua.p; b.obj_val = h->d_obj.p; b.work_counter = h->d_counter.p; b.prof = h->d_prof.p; b.active = h->active_src;
     CUDA_TRY(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     if (h->streamed) CUDA_TRY(launch_stream(h->ds, h->db, h->dst, h->dx, h->grid, h->smem_bytes, h->stream));
@@ -686,6 +687,24 @@ int gomp_batch_solve(gomp_batch *h) {
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     h->launches++;
     h->pending_flags = 0;
+    return GOMP_OK;
+}
+
+int gomp_batch_set_active(gomp_batch *h, const int32_t *active) {
+    if (!h) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!active) {
+        h->active_src = nullptr;
+        return GOMP_OK;
+    }
+    if (is_device_pointer(active) && h->st.borrow_inputs) {
+        h->active_src = active;
+        return GOMP_OK;
+    }
+    if (!h->d_active.p) CUDA_TRY(h->d_active.alloc((size_t)h->batch));
+    CUDA_TRY(cudaMemcpyAsync(h->d_active.p, active, (size_t)h->batch * sizeof(int),
+                             is_device_pointer(active) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    h->active_src = h->d_active.p;
     return GOMP_OK;
 }
 

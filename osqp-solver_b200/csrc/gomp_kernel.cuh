@@ -81,6 +81,7 @@ struct DevBatch {
     int *status, *iters, *rho_updates;
     double *pri_res, *dua_res, *obj_val;
     int *work_counter;
+    const int *active; // optional per-QP mask (NULL = all): QPs with 0 are skipped, their state and outputs stay
     unsigned long long *prof; // optional: per-phase cycle counters (thread 0 of every CTA adds), NULL = off
 };
 
@@ -809,6 +810,10 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_con
         __syncthreads();
         const int b = *sWork;
         if (b >= B.batch) break;
+        if (B.active != nullptr && B.active[b] == 0) { // masked out (converged SQP problem): nothing to do
+            __syncthreads();                          // everyone has read *sWork before it is overwritten
+            continue;
+        }
 
         if (!owner) {
             // SOLVER warps: wait for the owners' control word, then factor or substitute (separate function:

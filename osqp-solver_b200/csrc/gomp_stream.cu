@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
         const int b = *sWork;
         __syncthreads();
         if (b >= B.batch) break;
+        if (B.active != nullptr && B.active[b] == 0) continue; // masked out: state and outputs stay as they are
         const size_t bmu = (size_t)b * mu, bnp = (size_t)b * np;
         const bool hasq = B.q != nullptr;
         double *const gx = B.x_state + bnp, *const gz = B.z_state + bmu, *const gy = B.y_state + bmu;

@@ -18,7 +18,7 @@ EXIT_NAMES = ["kOptimal", "kPrimalInfeasible", "kDualInfeasible", "kOptimalInacc
               "kDualInfeasibleInaccurate", "kMaxIterations", "kInterrupted", "kTimeLimitReached", "kNonConvex", "kUnknown"]
 
 EXPORTS = ["gomp_settings_default", "gomp_batch_create", "gomp_batch_setup", "gomp_batch_warm_start_x", "gomp_batch_solve",
-           "gomp_batch_update", "gomp_batch_get", "gomp_batch_get_info", "gomp_batch_info", "gomp_batch_sync",
+           "gomp_batch_update", "gomp_batch_set_active", "gomp_batch_get", "gomp_batch_get_info", "gomp_batch_info", "gomp_batch_sync",
            "gomp_batch_destroy", "gomp_measure_peaks", "gomp_last_error_string", "gomp_device_count", "gomp_version"]
 
 
@@ -160,6 +160,12 @@ class BatchQPSolver:
         _check(lib().gomp_batch_update(self.h, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0]))
         if self.settings.borrow_inputs:
             self._borrowed = ptrs
+
+    def set_active(self, active):
+        """Mask for the following solves: int32 [batch] (numpy or torch CUDA tensor), None = all problems."""
+        p, keep = _ptr(active, dtype=np.int32)
+        _check(lib().gomp_batch_set_active(self.h, p))
+        self._active_keep = keep
 
     def solve_async(self):
         _check(lib().gomp_batch_solve(self.h))

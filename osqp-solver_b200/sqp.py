@@ -1,0 +1,82 @@
+"""Batched GOMPSolver::run for one horizon (reference src/gomp-solver.h:57-91) on the GPU.
+
+Every problem of the batch runs the reference's sequential-convex-programming loop
+
+    solve -> not kOptimal: give up | isSolutionOK: done | withObstacles(x) -> update -> again   (<= 100 rounds)
+
+with the data plane on the device: the QPs are solved by libgomp_cuda, the feasibility re-check and the
+re-linearisation are the kernels of gomp_relin.cu writing A_val / l / u in place, and a per-problem mask
+(gomp_batch_set_active) freezes problems that have finished while the others iterate.  The host sees three
+int32 per problem and round (exit code, ok flag, mask).  Needs torch for device buffers.
+"""
+import numpy as np
+
+from . import problem as _problem
+from . import solver as _solver
+
+MAX_ITERATIONS = 100  # reference src/gomp-solver.h:10
+K_OPTIMAL, K_UNKNOWN = 0, 10
+
+
+class BatchSQP:
+    def __init__(self, pattern, first_id, count, settings=None, device=None):
+        import torch
+        self.torch = torch
+        self.pattern, self.first_id, self.count = pattern, first_id, count
+        self.stream = torch.cuda.Stream()
+        st = settings if settings is not None else _solver.default_settings()
+        st.borrow_inputs = 1
+        st.stream = self.stream.cuda_stream
+        host = _problem.generate(pattern, first_id, count)
+        self.host = host
+        self.dev = {k: torch.from_numpy(host[k]).cuda() for k in ("A_val", "l", "u", "x0")}
+        self.solver = _solver.BatchQPSolver(pattern.n, pattern.m, pattern.P_colptr, pattern.P_rowidx, pattern.P_val,
+                                            pattern.A_colptr, pattern.A_rowidx, self.dev["A_val"], self.dev["l"], self.dev["u"],
+                                            batch=count, settings=st, var_order=pattern.var_order, block_size=pattern.block_size)
+        self.scene = _problem.DeviceScene(pattern, first_id, count)
+        self.x = torch.empty((count, pattern.n), dtype=torch.float64, device="cuda")
+        self.ok = torch.empty(count, dtype=torch.int32, device="cuda")
+        self.active = torch.ones(count, dtype=torch.int32, device="cuda")
+
+    def run(self, max_rounds=MAX_ITERATIONS):
+        """Returns dict(exit_code [count] (kOptimal / kUnknown as GOMPSolver::run reports them), qp_exit_code (the last
+        QP status of each problem), rounds [count] (QP solves used), x [count, n] torch CUDA tensor, total_qp_solves)."""
+        torch = self.torch
+        B = self.count
+        s = self.solver
+        s.set_warm_start(self.dev["x0"])
+        running = np.ones(B, dtype=bool)
+        code = np.full(B, K_UNKNOWN, dtype=np.int32)
+        qp_code = np.full(B, K_UNKNOWN, dtype=np.int32)
+        rounds = np.zeros(B, dtype=np.int32)
+        total = 0
+        self.active.fill_(1)
+        s.set_active(self.active)
+        sc = self.stream.cuda_stream
+        for rnd in range(max_rounds):
+            s.solve_async()
+            got = s.get(x=self.x)                          # x stays on the device; codes come to the host
+            self.scene.check(self.x, self.ok, stream=sc)
+            with torch.cuda.stream(self.stream):
+                ok = self.ok.cpu().numpy().astype(bool)     # (synchronises the stream)
+            total += int(running.sum())
+            rounds[running] += 1
+            qp_code[running] = got["exit_code"][running]
+            failed = running & (got["exit_code"] != K_OPTIMAL)          # gomp-solver.h:74-77: no solution for this horizon
+            done = running & ~failed & ok                               # :78-82
+            code[done] = K_OPTIMAL
+            running &= ~(failed | done)
+            if not running.any():
+                break
+            with torch.cuda.stream(self.stream):
+                self.active.copy_(torch.from_numpy(running.astype(np.int32)), non_blocking=False)
+            # :83-87 withObstacles + update for everybody still running (finished problems are masked out of the solve;
+            # re-linearising their rows is harmless and keeps the kernel branch-free)
+            self.scene.relinearize(self.x, self.dev["A_val"], self.dev["l"], self.dev["u"], x_fallback=self.dev["x0"], stream=sc)
+            s.update(self.dev["A_val"], self.dev["l"], self.dev["u"])
+        self.stream.synchronize()
+        return dict(exit_code=code, qp_exit_code=qp_code, rounds=rounds, x=self.x, total_qp_solves=total)
+
+    def close(self):
+        self.solver.close()
+        self.scene.close()

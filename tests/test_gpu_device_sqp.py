@@ -93,3 +93,39 @@ def test_sqp_sequence_stays_on_device():
     assert seen_active
     s.close()
     sc.close()
+
+
+def test_batched_sqp_driver_matches_per_problem_reference_loop():
+    """GOMPSolver::run for one horizon (reference src/gomp-solver.h:57-91) over a batch: per-problem exit code,
+    number of QP solves and trajectory equal those of the reference's loop run problem by problem on the CPU
+    (oracle QP solver + host withObstacles / isSolutionOK)."""
+    pkg, O = package(), oracle()
+    P = pkg.problem
+    pat = P.Pattern(P.default_config())
+    first, B, max_rounds = 0, 40, 12
+    drv = pkg.sqp.BatchSQP(pat, first, B)
+    out = drv.run(max_rounds=max_rounds)
+    x_dev = out["x"].cpu().numpy()
+    d = drv.host
+    Ps = pat.P_scipy()
+    for b in range(B):
+        ref = O.Solver(Ps, pat.A_scipy(d["A_val"][b]), d["l"][b], d["u"][b])
+        ref.warm_start_x(d["x0"][b])
+        code, rounds, x = 10, 0, None
+        for rnd in range(max_rounds):
+            ref.solve()
+            rounds += 1
+            x = ref.x
+            if ref.exit_code != 0:
+                break
+            if P.check(pat, first + b, x[None, :])[0]:
+                code = 0
+                break
+            upd = P.relinearize(pat, first + b, x[None, :])
+            ref.update(upd["A_val"][0], upd["l"][0], upd["u"][0])
+        assert out["exit_code"][b] == code, (b, out["exit_code"][b], code)
+        assert out["rounds"][b] == rounds, (b, out["rounds"][b], rounds)
+        if code == 0:
+            assert np.abs(x_dev[b] - x).max() < 1e-6 * np.abs(x).max()
+    assert (out["exit_code"] == 0).sum() >= B // 2 and (out["rounds"] > 1).any() and len(set(out["rounds"].tolist())) > 1
+    drv.close()
