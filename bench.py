@@ -86,6 +86,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# batches in flight per GPU: consecutive steps rotate over PIPE solver handles / streams (measured on B200:
+# 2 -> 107 k, 4 -> 130 k, 6 -> 142 k, 8 -> 142 k QP/s); every step still is a full cold setup + warm start + solve
+PIPE = int(os.environ.get("GOMP_BENCH_PIPE", "6"))
+
+
 def workload(pkg):
     P = pkg.problem
     cfg = P.default_config()
@@ -95,7 +100,7 @@ def workload(pkg):
                         "(eps 1e-3, adaptive_rho_interval pinned to 25)",
             "n_dim": 7, "waypoints": 50, "n": pat.n, "m": pat.m, "nnzA": pat.nnzA, "batch_per_gpu": BATCH_PER_GPU,
             "l2_policy": "inputs larger than L2 (305 MB of A_val/l/u per step vs 126 MB L2)",
-            "batches_in_flight": 4}
+            "batches_in_flight": PIPE}
     return cfg, pat, desc
 
 
@@ -155,10 +160,9 @@ def run_gpu(args):
             dict(A_val=(B, pat.nnzA), l=(B, pat.m), u=(B, pat.m), x0=(B, pat.n), start_goal=(B, 2 * cfg.n_dim)).items()}
     pkg.problem.generate(pat, first_id, B, out={k: v.numpy() for k, v in host.items()})
     dev = {k: host[k].cuda() for k in ("A_val", "l", "u", "x0")}
-    # Four batches in flight: consecutive steps rotate over four handles on four streams, so the few
+    # PIPE batches in flight: consecutive steps rotate over PIPE handles on PIPE streams, so the few
     # QPs of a batch that need thousands of ADMM iterations (max_iter = 4000) overlap with the next batch
     # instead of leaving 146 SMs idle.  Every step still is a full cold setup + warm start + solve.
-    PIPE = 4
     streams = [torch.cuda.Stream() for _ in range(PIPE)]
     main = torch.cuda.current_stream()
 
@@ -354,8 +358,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="gomp_cuda", choices=["gomp_cuda", "reference"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

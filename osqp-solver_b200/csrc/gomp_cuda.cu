@@ -797,8 +797,10 @@ int gomp_batch_info(gomp_batch *h, gomp_info *info) {
             info->phase_cycles[2] += (double)pc[8]; // assembly is reported inside 'factor'
             info->assemble_cycles = (double)pc[8];
             info->chain_cycles = (double)pc[9];
-            if (std::getenv("GOMP_PROFILE_PHASES")[0] == '2')
+            if (std::getenv("GOMP_PROFILE_PHASES")[0] == '2') {
                 std::fprintf(stderr, "chain marks (cycles): [10] %.0f  [11] %.0f  [12] %.0f  total %.0f\n", (double)pc[10], (double)pc[11], (double)pc[12], (double)pc[9]);
+                std::fprintf(stderr, "info marks (cycles): rows %.0f  cols %.0f  termination %.0f\n", (double)pc[13], (double)pc[14], (double)pc[15]);
+            }
     }
     info->last_solve_ms = h->last_solve_ms;
     info->last_h2d_ms = h->last_h2d_ms;

@@ -557,6 +557,7 @@ __device__ __forceinline__ double row_rest4(const uint32_t *__restrict__ ent, ui
                                             const double *__restrict__ vec, double acc) {
     int q = (int)(range >> 8) + 4;
     const int q1 = (int)(range >> 8) + (int)(range & 0xFFu);
+#pragma unroll 1 // (the compiler would unroll this by four at every inlined site: code size, not speed)
     for (; q < q1; q += 4) {
         const uint32_t e0 = ent[q], e1 = ent[q + 1], e2 = ent[q + 2], e3 = ent[q + 3];
         const double a0 = A[e0 & 0xFFFFu], a1 = A[e1 & 0xFFFFu], a2 = A[e2 & 0xFFFFu], a3 = A[e3 & 0xFFFFu];
@@ -579,6 +580,7 @@ __device__ __forceinline__ double col_dot4(uint32_t range, const double *__restr
                                            const double *__restrict__ vec, double acc) {
     int k = (int)(range >> 8);
     const int k1 = k + (int)(range & 0xFFu);
+#pragma unroll 1
     for (; k < k1; k += 4) {
         const int r0 = rowOf[k], r1 = rowOf[k + 1], r2 = rowOf[k + 2], r3 = rowOf[k + 3];
         const double a0 = A[k], a1 = A[k + 1], a2 = A[k + 2], a3 = A[k + 3];
@@ -1064,6 +1066,15 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_con
 
             if (do_info) {
                 // ---------------- residuals and the norms OSQP's tolerances need (update_info)
+                long long t_info = clock64();
+#define INFO_MARK(slot)                                                              \
+    do {                                                                             \
+        if (B.prof != nullptr && tid == kSolverThreads) {                            \
+            const long long now__ = clock64();                                       \
+            atomicAdd(&B.prof[slot], (unsigned long long)(now__ - t_info));          \
+            t_info = now__;                                                          \
+        }                                                                            \
+    } while (0)
                 COLS_LOOP(c, p) sRHS[p] = x[c];
                 ROWS_LOOP(j, i) sW[i] = y[j];
                 w_dirty = true;
@@ -1084,6 +1095,7 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_con
                     }
                     owners_max<6>(na, sRed, oid);
                     pri_u = na[0]; pri_s = na[1]; pn_u = fmax(na[2], na[3]); pn_s = fmax(na[4], na[5]);
+                    INFO_MARK(13);
                 }
                 {
                     double nb[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -1105,6 +1117,7 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_con
                     }
                     owners_max<8>(nb, sRed, oid);
                     dua_u = nb[0]; dua_s = nb[1]; dn_u = fmax(nb[4], fmax(nb[3], nb[2])); dn_s = fmax(nb[7], fmax(nb[6], nb[5]));
+                    INFO_MARK(14);
                 }
                 pri_res = uns ? pri_u : pri_s;
                 dua_res = uns ? cinv * dua_u : dua_s;
@@ -1224,6 +1237,8 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_con
                     }
                 }
                 if (!done && last) status = -2;
+                INFO_MARK(15);
+#undef INFO_MARK
                 PHASE_MARK(PH_INFO);
             }
         }
