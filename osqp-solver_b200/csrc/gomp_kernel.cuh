@@ -490,6 +490,44 @@ __device__ __forceinline__ void factor_block_group(const DevSym &S, unsigned cha
             val[q] -= acc;
         }
     }
+    if (BS > 0 && BS <= 16 && BS % 2 == 0 && EPL == 1) {
+        // Gauss-Jordan sweeps with 2x2 pivot blocks (SPD block, no pivoting): half the barriers and half the
+        // dependent reciprocal chains of the scalar version below.  Sweep of the index pair K = {k, k+1}:
+        //   M_KK <- P^-1,  M_Kj <- P^-1 M_Kj,  M_iK <- -M_iK P^-1,  M_ij <- M_ij - M_iK P^-1 M_Kj
+        // with P^-1 = adj(P) / det(P); everything but the final scaling by 1/det is independent of the division.
+        const int i = ri[0], j = ci[0];
+        double v = val[0];
+#pragma unroll 1
+        for (int k = 0; k < BS; k += 2) {
+            double *buf = pub + ((k >> 1) & 1) * 64; // [row k | row k+1 | column k | column k+1], 16 doubles each
+            if (i >= 0) {
+                if (i == k) buf[j] = v;
+                if (i == k + 1) buf[16 + j] = v;
+                if (j == k) buf[32 + i] = v;
+                if (j == k + 1) buf[48 + i] = v;
+            }
+            named_bar_sync(4 + g, kFactorGroup);
+            if (i < 0) continue;
+            const double a = buf[k], b = buf[k + 1], c = buf[16 + k], d = buf[16 + k + 1]; // P = [a b; c d]
+            const double r1 = buf[j], r2 = buf[16 + j];                                     // M_Kj
+            const double c1 = buf[32 + i], c2 = buf[48 + i];                                // M_iK
+            const double invdet = 1.0 / (a * d - b * c);
+            const bool ik = (i >> 1) == (k >> 1), jk = (j >> 1) == (k >> 1);
+            const double u1 = d * r1 - b * r2, u2 = a * r2 - c * r1; // adj(P) M_Kj
+            if (!ik && !jk) {
+                v = fma(-(c1 * u1 + c2 * u2), invdet, v);
+            } else if (ik && !jk) {
+                v = (i == k ? u1 : u2) * invdet;
+            } else if (!ik && jk) {
+                const double w1 = c1 * d - c2 * c, w2 = c2 * a - c1 * b; // M_iK adj(P)
+                v = -((j == k ? w1 : w2) * invdet);
+            } else {
+                const double adj = i == k ? (j == k ? d : -b) : (j == k ? -c : a);
+                v = adj * invdet;
+            }
+        }
+        val[0] = v;
+    } else
     // Gauss-Jordan without pivoting (SPD block), entries in registers
 #pragma unroll 1
     for (int k = 0; k < bs; ++k) {
@@ -518,8 +556,10 @@ __device__ __forceinline__ void factor_block_group(const DevSym &S, unsigned cha
 }
 
 // phase 0: both chains (threads 0..447);  phase 1: the middle stage (group 0) after a CTA-wide barrier
+// One shared out-of-line copy: the factorisation runs once or twice per QP, from both roles; keeping it out of the
+// callers keeps their hot loops (substitution sweeps, gather / update) compact and their layout independent of it.
 template <int BS>
-__device__ __forceinline__ void factor_cooperative(const DevSym &S, unsigned char *smem_raw, int tid, int phase) {
+static __device__ __noinline__ void factor_cooperative(const DevSym &S, unsigned char *smem_raw, int tid, int phase) {
     if (tid >= 2 * kFactorGroup) return;
     const int g = tid / kFactorGroup, gl = tid - g * kFactorGroup;
     const int T = S.T, h = S.T / 2;

@@ -256,6 +256,41 @@ __device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dal
             val[q] -= acc;
         }
     }
+    if (BS > 0 && BS <= 16 && BS % 2 == 0 && EPL == 1) {
+        // Gauss-Jordan sweeps with 2x2 pivot blocks, as in the resident kernel (gomp_kernel.cuh, factor_block_group)
+        const int i = ri[0], j = ci[0];
+        double v = val[0];
+#pragma unroll 1
+        for (int k = 0; k < BS; k += 2) {
+            double *buf = pub + ((k >> 1) & 1) * 64; // [row k | row k+1 | column k | column k+1], 16 doubles each
+            if (i >= 0) {
+                if (i == k) buf[j] = v;
+                if (i == k + 1) buf[16 + j] = v;
+                if (j == k) buf[32 + i] = v;
+                if (j == k + 1) buf[48 + i] = v;
+            }
+            named_bar_sync(4 + g, kGroup);
+            if (i < 0) continue;
+            const double a = buf[k], b = buf[k + 1], c = buf[16 + k], d = buf[16 + k + 1];
+            const double r1 = buf[j], r2 = buf[16 + j];
+            const double c1 = buf[32 + i], c2 = buf[48 + i];
+            const double invdet = 1.0 / (a * d - b * c);
+            const bool ik = (i >> 1) == (k >> 1), jk = (j >> 1) == (k >> 1);
+            const double u1 = d * r1 - b * r2, u2 = a * r2 - c * r1;
+            if (!ik && !jk) {
+                v = fma(-(c1 * u1 + c2 * u2), invdet, v);
+            } else if (ik && !jk) {
+                v = (i == k ? u1 : u2) * invdet;
+            } else if (!ik && jk) {
+                const double w1 = c1 * d - c2 * c, w2 = c2 * a - c1 * b;
+                v = -((j == k ? w1 : w2) * invdet);
+            } else {
+                const double adj = i == k ? (j == k ? d : -b) : (j == k ? -c : a);
+                v = adj * invdet;
+            }
+        }
+        val[0] = v;
+    } else
 #pragma unroll 1
     for (int k = 0; k < bs; ++k) { // Gauss-Jordan without pivoting (SPD block)
         double *rowk = pub + (k & 1) * 64, *colk = rowk + 32;
