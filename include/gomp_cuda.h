@@ -162,6 +162,18 @@ int gomp_batch_get_info(gomp_batch *h, double *pri_res, double *dua_res, double 
  * converged or failed while others still iterate. */
 int gomp_batch_set_active(gomp_batch *h, const int32_t *active);
 
+/* Device-side views of a handle, for callers that keep an SQP round on the GPU without linking the CUDA runtime
+ * themselves (gomp_problem.h, device section): the handle's own copies of A_val / l / u (NULL while that input is
+ * borrowed from the caller), the primal results of the last solve [batch, n] and the stream all of the handle's
+ * work is ordered on.  Any out-pointer may be NULL.  After rewriting A_val / l / u in place on that stream, call
+ * gomp_batch_update with the same pointers: nothing is copied, the next solve re-scales and re-factors. */
+int gomp_batch_device_views(gomp_batch *h, double **A_val, double **l, double **u, const double **x, void **stream);
+
+/* Plain device-memory helpers for such callers: allocate / free / copy (cudaMemcpyDefault on `stream`, then wait). */
+int gomp_device_malloc(void **ptr, int64_t bytes, int32_t device);
+int gomp_device_free(void *ptr);
+int gomp_device_memcpy(void *dst, const void *src, int64_t bytes, void *stream);
+
 int gomp_batch_info(gomp_batch *h, gomp_info *info);
 int gomp_batch_sync(gomp_batch *h);
 int gomp_batch_destroy(gomp_batch *h);

@@ -316,6 +316,10 @@ int stage_input(gomp_batch *h, const double *src, DevArray<double> &dst, size_t 
         CUDA_TRY(dst.alloc(count));
         h->workspace_bytes += count * sizeof(double);
     }
+    if (src == dst.p) { // the caller rewrote the handle's own copy in place (gomp_batch_device_views)
+        *use = dst.p;
+        return GOMP_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(dst.p, src, count * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                              h->stream));
     *use = dst.p;
@@ -705,6 +709,36 @@ int gomp_batch_set_active(gomp_batch *h, const int32_t *active) {
     CUDA_TRY(cudaMemcpyAsync(h->d_active.p, active, (size_t)h->batch * sizeof(int),
                              is_device_pointer(active) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     h->active_src = h->d_active.p;
+    return GOMP_OK;
+}
+
+int gomp_batch_device_views(gomp_batch *h, double **A_val, double **l, double **u, const double **x, void **stream) {
+    if (!h) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
+    if (A_val) *A_val = h->A_src == h->d_A.p ? h->d_A.p : nullptr;
+    if (l) *l = h->l_src == h->d_l.p ? h->d_l.p : nullptr;
+    if (u) *u = h->u_src == h->d_u.p ? h->d_u.p : nullptr;
+    if (x) *x = h->d_xo.p;
+    if (stream) *stream = (void *)h->stream;
+    return GOMP_OK;
+}
+
+int gomp_device_malloc(void **ptr, int64_t bytes, int32_t device) {
+    if (!ptr || bytes < 0) return fail(GOMP_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (gomp_device_count() <= 0) return fail(GOMP_ERR_NO_DEVICE, "no CUDA device visible");
+    if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMalloc(ptr, (size_t)std::max<int64_t>(bytes, 1)));
+    return GOMP_OK;
+}
+
+int gomp_device_free(void *ptr) {
+    if (ptr) CUDA_TRY(cudaFree(ptr));
+    return GOMP_OK;
+}
+
+int gomp_device_memcpy(void *dst, const void *src, int64_t bytes, void *stream) {
+    if (!dst || !src || bytes < 0) return fail(GOMP_ERR_INVALID_ARGUMENT, "bad arguments");
+    CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return GOMP_OK;
 }
 

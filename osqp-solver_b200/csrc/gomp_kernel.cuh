@@ -636,7 +636,7 @@ __device__ __forceinline__ double col_dot4(uint32_t range, const double *__restr
 // Assembly of S = P + sigma I + A' diag(rho) A into the full-row pivot blocks and the ELL
 // off-diagonal blocks; destination driven (deterministic, no atomics), every thread of the CTA helps.
 // sW holds rho per compact row.
-__device__ __forceinline__ void assemble_S(const DevSym &S, double sigma, const double *sW, const double *sA, const double *sP,
+static __device__ __noinline__ void assemble_S(const DevSym &S, double sigma, const double *sW, const double *sA, const double *sP,
                                                double *sDinv, double *sOff, int tid, int bs) {
     const int dpb = bs * (bs + 1) / 2, ndiag = S.T * dpb, bb = bs * bs;
     for (int e = tid; e < ndiag; e += kThreads) {

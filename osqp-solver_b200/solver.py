@@ -19,7 +19,8 @@ EXIT_NAMES = ["kOptimal", "kPrimalInfeasible", "kDualInfeasible", "kOptimalInacc
 
 EXPORTS = ["gomp_settings_default", "gomp_batch_create", "gomp_batch_setup", "gomp_batch_warm_start_x", "gomp_batch_solve",
            "gomp_batch_update", "gomp_batch_set_active", "gomp_batch_get", "gomp_batch_get_info", "gomp_batch_info", "gomp_batch_sync",
-           "gomp_batch_destroy", "gomp_measure_peaks", "gomp_last_error_string", "gomp_device_count", "gomp_version"]
+           "gomp_batch_destroy", "gomp_batch_device_views", "gomp_device_malloc", "gomp_device_free", "gomp_device_memcpy",
+           "gomp_measure_peaks", "gomp_last_error_string", "gomp_device_count", "gomp_version"]
 
 
 class Settings(C.Structure):

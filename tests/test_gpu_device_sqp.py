@@ -129,3 +129,24 @@ def test_batched_sqp_driver_matches_per_problem_reference_loop():
             assert np.abs(x_dev[b] - x).max() < 1e-6 * np.abs(x).max()
     assert (out["exit_code"] == 0).sum() >= B // 2 and (out["rounds"] > 1).any() and len(set(out["rounds"].tolist())) > 1
     drv.close()
+
+
+def test_cpp_batch_solver_matches_python_driver():
+    """GOMPBatchSolver (osqp-solver_b200/include/gomp/gomp-batch-solver.h: host C++ over the two C ABIs, no CUDA
+    headers) gives the same per-problem exit codes and round counts as sqp.BatchSQP."""
+    import os
+    import subprocess
+    from common import ROOT
+    pkg = package()
+    P = pkg.problem
+    pkg_dir = os.path.join(ROOT, "osqp-solver_b200")
+    exe = os.path.join(pkg_dir, "build", "batch-sqp-example")
+    subprocess.check_call(["make", "-C", pkg_dir, "example"], stdout=subprocess.DEVNULL)
+    B, first, max_rounds = 48, 100, 10
+    out = subprocess.run([exe, str(B), str(first), str(max_rounds)], capture_output=True, text=True, check=True).stdout.splitlines()
+    pairs = [tuple(int(v) for v in tok.split(":")) for tok in out[1].split()[1:]]
+    drv = pkg.sqp.BatchSQP(P.Pattern(P.default_config()), first, B)
+    ref = drv.run(max_rounds=max_rounds)
+    drv.close()
+    assert pairs == list(zip(ref["exit_code"].tolist(), ref["rounds"].tolist()))
+    assert f"qp_solves {ref['total_qp_solves']}" in out[0]
