@@ -80,3 +80,49 @@ class BatchSQP:
     def close(self):
         self.solver.close()
         self.scene.close()
+
+
+SEGMENTS = 10  # reference src/gomp-solver.h:11
+
+
+def shortest_horizon(cfg, first_id, count, max_rounds=MAX_ITERATIONS, settings_factory=None):
+    """GOMPSolver::run(start, goal) -- the time-shrink outer loop of reference src/gomp-solver.h:38-55 -- for a batch.
+
+    The reference solves the horizons W*i/SEGMENTS, i = SEGMENTS..1, one after the other, keeps the last kOptimal
+    trajectory and stops at the first horizon whose QP fails.  Given a warm start the horizons are independent, so
+    here every horizon is one batch over all problems (BatchSQP; long ones run on the streamed back end) and the
+    reference's selection rule is applied per problem afterwards.  Difference to the reference, on purpose: each
+    horizon starts from its own straight-line warm start instead of the previous horizon's sliced solution
+    (gomp-solver.h:43-44), which is what makes them independent.
+
+    Returns dict(exit_code [count], waypoints [count] (horizon of the returned trajectory, 0 = none),
+    x (list of per-problem numpy trajectories, velocities per second as the reference returns them), horizons,
+    qp_solves)."""
+    import copy
+    W = cfg.waypoints
+    horizons = [W * i // SEGMENTS for i in range(SEGMENTS, 0, -1) if W * i // SEGMENTS >= 4]
+    per_h = []
+    total = 0
+    for w in horizons:
+        c = copy.copy(cfg)
+        c.waypoints = w
+        pat = _problem.Pattern(c)
+        drv = BatchSQP(pat, first_id, count, settings=settings_factory() if settings_factory else None)
+        out = drv.run(max_rounds=max_rounds)
+        per_h.append(dict(code=out["exit_code"].copy(), x=out["x"].cpu().numpy(), n=pat.n))
+        total += out["total_qp_solves"]
+        drv.close()
+    code = np.full(count, K_UNKNOWN, dtype=np.int32)
+    chosen = np.zeros(count, dtype=np.int32)
+    xs = [None] * count
+    for b in range(count):
+        for w, res in zip(horizons, per_h):
+            ec = res["code"][b]
+            if ec != K_OPTIMAL and ec != K_UNKNOWN:   # gomp-solver.h:46-47 (BatchSQP only reports these two: kept for fidelity)
+                break
+            if ec == K_OPTIMAL:                        # :48-51
+                code[b], chosen[b] = K_OPTIMAL, w
+                x = res["x"][b].copy()
+                x[res["n"] // 2:] /= cfg.time_step     # :52-54 velocities per second
+                xs[b] = x
+    return dict(exit_code=code, waypoints=chosen, x=xs, horizons=horizons, qp_solves=total)

@@ -150,3 +150,29 @@ def test_cpp_batch_solver_matches_python_driver():
     drv.close()
     assert pairs == list(zip(ref["exit_code"].tolist(), ref["rounds"].tolist()))
     assert f"qp_solves {ref['total_qp_solves']}" in out[0]
+
+
+def test_shortest_horizon_batch():
+    """Time-shrink outer loop (reference src/gomp-solver.h:38-55) as one batch per horizon: the returned horizon is
+    the shortest kOptimal one, its trajectory passes the host isSolutionOK at that horizon, and horizons longer than
+    the resident kernel's limit run on the streamed back end."""
+    pkg = package()
+    P = pkg.problem
+    cfg = P.default_config(waypoints=80)
+    B = 12
+    out = pkg.sqp.shortest_horizon(cfg, 300, B, max_rounds=8)
+    assert out["horizons"] == [80, 72, 64, 56, 48, 40, 32, 24, 16, 8]
+    assert (out["exit_code"] == 0).sum() >= B // 2
+    import copy
+    for b in range(B):
+        if out["exit_code"][b] != 0:
+            assert out["waypoints"][b] == 0 and out["x"][b] is None
+            continue
+        w = int(out["waypoints"][b])
+        c = copy.copy(cfg)
+        c.waypoints = w
+        pat = P.Pattern(c)
+        x = out["x"][b].copy()
+        assert x.shape == (pat.n,)
+        x[pat.n // 2:] *= cfg.time_step   # back to per-step velocities for the check
+        assert P.check(pat, 300 + b, x[None, :])[0]
