@@ -556,7 +556,10 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
         };
         x.slot_doubles = s.bs * s.bs + s.bs * s.ow;
         x.oRHS = take(8 * (size_t)s.n_pad);
-        x.ring_doubles = std::max(kStreamRing, kStreamGroup * kStreamGroupRing) * x.slot_doubles;
+        // the grouped ring (fast path of gomp_stream.cu: compile-time block size 14, uniform 2-wide off-diagonal pattern)
+        // needs kStreamGroup * kStreamGroupRing stage slots per warp, the generic path kStreamRing
+        const bool grouped = s.bs == 14 && h->ds.uniform_off && s.ow <= 2 && s.owT <= 2;
+        x.ring_doubles = (grouped ? std::max(kStreamRing, kStreamGroup * kStreamGroupRing) : kStreamRing) * x.slot_doubles;
         x.oRing = take(8 * (size_t)2 * x.ring_doubles);
         x.oPub = take(8 * 256);
         x.oDprev = take(8 * (size_t)2 * s.bs * s.bs);

@@ -107,3 +107,27 @@ def test_non_block_tridiagonal_order_is_rejected():
     with pytest.raises(ValueError):
         emul.Emulator(1, pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx, O.default_settings(),
                       var_order=np.arange(pat.n), block_size=pat.block_size)  # [all q | all v] order is not block tridiagonal
+
+
+@pytest.mark.parametrize("bs,T", [(3, 5), (6, 9), (10, 12), (16, 7), (32, 3), (5, 1), (4, 2)])
+def test_random_block_tridiagonal_qps(bs, T):
+    """Generic patterns (no GOMP structure): random block sizes / chain lengths, q != 0, all row types."""
+    from common import random_block_qp
+    pkg, O = package(), oracle()
+    rng = np.random.default_rng(100 * bs + T)
+    B = 4
+    P, A, Ax, l, u, q = random_block_qp(rng, bs, T, B)
+    n, m = P.shape[0], A.shape[0]
+    st = O.default_settings(eps_abs=1e-6, eps_rel=1e-6)
+    E = emul.Emulator(B, n, m, P.indptr, P.indices, P.data, A.indptr, A.indices, st, var_order=np.arange(n), block_size=bs)
+    assert (E.bs, E.T) == (bs, T)
+    E.set_data(Ax, l, u, q)
+    got = E.solve()
+    for b in range(B):
+        Ab = sp.csc_matrix((Ax[b], A.indices, A.indptr), shape=(m, n))
+        r = O.Solver(P, Ab, l[b], u[b], q=q[b], settings=st)
+        r.solve()
+        assert got["exit_code"][b] == r.exit_code and got["iters"][b] == r.iter and got["rho_updates"][b] == r.rho_updates
+        if r.exit_code == 0:
+            assert np.abs(got["x"][b] - r.x).max() < 1e-6 * max(1.0, np.abs(r.x).max())
+            assert np.abs(got["y"][b] - r.y).max() < 1e-6 * max(1.0, np.abs(r.y).max())

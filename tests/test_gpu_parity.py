@@ -295,3 +295,35 @@ def test_full_size_batch_properties(env):
     np.testing.assert_array_equal(r["x"], r2["x"])
     np.testing.assert_array_equal(r["iters"], r2["iters"])
     s.close()
+
+
+@pytest.mark.parametrize("linsys", [0, 2])
+@pytest.mark.parametrize("bs,T", [(3, 5), (6, 9), (10, 12), (16, 7), (32, 3), (5, 1), (4, 2), (14, 20), (2, 40)])
+def test_random_block_tridiagonal_qps(bs, T, linsys):
+    """Generic patterns on both back ends (resident kernel variants 2_1_0 / 4_2_0 / 8_4_0 with run-time block size;
+    streamed kernel for even block sizes): random block sizes and chain lengths, q != 0, equality / loose /
+    one-sided / empty rows.  Same bar as the GOMP shapes: equal status, iterations, rho updates; x, y to 1e-6."""
+    from common import random_block_qp
+    if linsys == 2 and bs % 2:
+        pytest.skip("streamed back end needs an even block size (16-byte bulk copies)")
+    pkg, O = package(), oracle()
+    rng = np.random.default_rng(100 * bs + T)
+    B = 6
+    P, A, Ax, l, u, q = random_block_qp(rng, bs, T, B)
+    n, m = P.shape[0], A.shape[0]
+    st = pkg.solver.default_settings(eps_abs=1e-6, eps_rel=1e-6, linsys=linsys)
+    s = pkg.solver.BatchQPSolver(n, m, P.indptr, P.indices, P.data, A.indptr, A.indices, Ax, l, u, q=q, settings=st,
+                                 var_order=np.arange(n), block_size=bs)
+    info = s.info()
+    assert (info["block_size"], info["num_blocks"]) == (bs, T) and info["linsys"] == (2 if linsys == 2 else 1)
+    got = s.solve(want_y=True)
+    s.close()
+    ost = O.default_settings(eps_abs=1e-6, eps_rel=1e-6)
+    for b in range(B):
+        Ab = sp.csc_matrix((Ax[b], A.indices, A.indptr), shape=(m, n))
+        r = O.Solver(P, Ab, l[b], u[b], q=q[b], settings=ost)
+        r.solve()
+        assert got["exit_code"][b] == r.exit_code and got["iters"][b] == r.iter and got["rho_updates"][b] == r.rho_updates
+        if r.exit_code == 0:
+            assert np.abs(got["x"][b] - r.x).max() < REL_TOL * max(1.0, np.abs(r.x).max())
+            assert np.abs(got["y"][b] - r.y).max() < REL_TOL * max(1.0, np.abs(r.y).max())
