@@ -357,6 +357,93 @@ __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st
 // is the off-diagonal block tb = t + tbo (its transpose when the per-lane offsets describe a column).
 // Per-lane pattern constants (uniform over the stages): g0/g1 source lanes, o0/o1 byte offsets of the two
 // values inside block tb, has0/has1.  Returns the last stage's result.
+template <int BS, bool fwd>
+__device__ __forceinline__ double chain_sweep_impl(uint32_t dinv0, uint32_t rhs0, uint32_t off0, uint32_t vb0, int t0, int count, int dir,
+                                                   int tbo, int nblk, uint32_t blk_bytes, double prev, int lane, int g0, int g1,
+                                                   uint32_t o0, uint32_t o1, bool has0, bool has1) {
+    // Two lanes per block row: lane = r + 16*half; half 0 multiplies columns [0, CH), half 1 columns [CH, NB);
+    // CH is even so both halves start 16-byte aligned.  Halves the loads and FMAs each lane issues per step.
+    constexpr int NB = BS > 0 ? BS : 2;
+    constexpr int CH = ((NB / 2) + 1) & ~1;              // 8 for NB = 14
+    constexpr int NC = CH > NB - CH ? CH : NB - CH;       // columns a lane handles at most
+    const int r = lane & 15, half = lane >> 4;
+    const int rl = r < NB ? r : NB - 1;
+    const bool act = half == 0 && r < NB;                 // the lane that owns row r's scalar work
+    const int c0 = half ? CH : 0, nc = half ? NB - CH : CH;
+    // running shared-window addresses (one add per stage instead of re-deriving them from the stage index)
+    uint32_t arow = dinv0 + (uint32_t)((t0 * NB + rl) * NB + c0) * 8u; // this lane's half row of the stage's inverse
+    uint32_t ab = rhs0 + (uint32_t)(t0 * NB + rl) * 8u;                 // its right-hand side entry
+    int tb = t0 + tbo;                                                   // off-diagonal block of the stage
+    uint32_t ao = off0 + (uint32_t)tb * blk_bytes;                       // (only dereferenced when 0 <= tb < nblk)
+    uint32_t par = (uint32_t)(t0 & 1) * 128u;                            // double-buffered broadcast line: vb0 + 0 / + 128
+    const uint32_t darow = (uint32_t)(dir * NB * NB * 8), dab = (uint32_t)(dir * NB * 8), dao = (uint32_t)dir * blk_bytes;
+#pragma unroll 1
+    for (int it = 0; it < count; ++it) {
+        // ---- independent of the previous stage
+        double m[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c += 2) {
+            if (c < nc) {
+                const double2 d = lds_f64x2(arow + (uint32_t)c * 8u);
+                m[c] = d.x;
+                m[c + 1] = d.y;
+            } else {
+                m[c] = 0.0;
+                m[c + 1] = 0.0;
+            }
+        }
+        const double b = lds_f64(ab);
+        const bool blk = (unsigned)tb < (unsigned)nblk;
+        const double ov0 = (blk && has0) ? lds_f64(ao + o0) : 0.0;
+        const double ov1 = (blk && has1) ? lds_f64(ao + o1) : 0.0;
+        // ---- dependent chain (prev[r] is held by both lanes of row r; sources are lanes < 16)
+        const double up0 = __shfl_sync(0xffffffffu, prev, g0);
+        const double up1 = __shfl_sync(0xffffffffu, prev, g1);
+        const double off = fma(ov0, up0, ov1 * up1);
+        const double v = fwd ? b - off : off;
+        const uint32_t avb = vb0 + par;
+        if (act) sts_f64(avb + (uint32_t)r * 8u, v);
+        __syncwarp();
+        double2 w[NC / 2];
+#pragma unroll
+        for (int c = 0; c < NC; c += 2) w[c / 2] = c < nc ? lds_f64x2(avb + (uint32_t)(c0 + c) * 8u) : make_double2(0.0, 0.0);
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; c += 2) {
+            a0 = fma(m[c], w[c / 2].x, a0);
+            a1 = fma(m[c + 1], w[c / 2].y, a1);
+        }
+        double acc = a0 + a1;
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        prev = fwd ? acc : b - acc;
+        if (act) sts_f64(ab, prev);
+        arow += darow;
+        ab += dab;
+        ao += dao;
+        tb += dir;
+        par ^= 128u;
+    }
+    return prev;
+}
+// Out-of-line instances (one per sweep direction of the recurrence): scheduled and register-allocated on their own,
+// whatever surrounds the call -- the inlined copies lost 20-30 % to the code around them.
+template <int BS, bool fwd>
+static __device__ __noinline__ double chain_sweep_call(uint32_t dinv0, uint32_t rhs0, uint32_t off0, uint32_t vb0, int t0, int count, int dir,
+                                                       int tbo, int nblk, uint32_t blk_bytes, double prev, int lane, int g0, int g1,
+                                                       uint32_t o0, uint32_t o1, bool has0, bool has1) {
+    return chain_sweep_impl<BS, fwd>(dinv0, rhs0, off0, vb0, t0, count, dir, tbo, nblk, blk_bytes, prev, lane, g0, g1, o0, o1, has0, has1);
+}
+// (used by the streamed kernel, where the out-of-line instances are 10 % faster than inlined copies; the resident
+// kernel keeps the inlined chain_sweep below, which is the faster one inside solver_role)
+template <int BS>
+__device__ __forceinline__ double chain_sweep_ool(uint32_t dinv0, uint32_t rhs0, uint32_t off0, uint32_t vb0, int t0, int count, int dir,
+                                                  int tbo, int nblk, uint32_t blk_bytes, bool fwd, double prev, int lane, int g0, int g1,
+                                                  uint32_t o0, uint32_t o1, bool has0, bool has1) {
+    return fwd ? chain_sweep_call<BS, true>(dinv0, rhs0, off0, vb0, t0, count, dir, tbo, nblk, blk_bytes, prev, lane, g0, g1, o0, o1, has0, has1)
+               : chain_sweep_call<BS, false>(dinv0, rhs0, off0, vb0, t0, count, dir, tbo, nblk, blk_bytes, prev, lane, g0, g1, o0, o1, has0, has1);
+}
+
+// Inlined form of the same sweep (stage addresses derived from the stage index), as used by solver_role.
 template <int BS>
 __device__ __forceinline__ double chain_sweep(uint32_t dinv0, uint32_t rhs0, uint32_t off0, uint32_t vb0, int t0, int count, int dir,
                                               int tbo, int nblk, uint32_t blk_bytes, bool fwd, double prev, int lane, int g0, int g1,

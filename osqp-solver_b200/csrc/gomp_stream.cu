@@ -342,15 +342,6 @@ __device__ __forceinline__ Step step_of(int warp, int j, int T, int h) {
     return s;
 }
 
-// Out-of-line instance of the resident kernel's sweep: one copy, scheduled on its own, whatever surrounds the call
-// (measured: 171 k cycles per H=400 block solve against 172-188 k for the inlined copies, depending on the build).
-template <int BS>
-static __device__ __noinline__ double chain_sweep_call(uint32_t dinv0, uint32_t rhs0, uint32_t off0, uint32_t vb0, int t0, int count, int dir,
-                                                       int tbo, int nblk, uint32_t blk_bytes, bool fwd, double prev, int lane, int g0, int g1,
-                                                       uint32_t o0, uint32_t o1, bool has0, bool has1) {
-    return chain_sweep<BS>(dinv0, rhs0, off0, vb0, t0, count, dir, tbo, nblk, blk_bytes, fwd, prev, lane, g0, g1, o0, o1, has0, has1);
-}
-
 #define SMARK(ph)                                                                   \
     do {                                                                            \
         if (B.prof != nullptr && tid == 0) {                                        \
@@ -752,7 +743,7 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                         const uint32_t dinv0 = sl - (uint32_t)(tlo * bb) * 8u;                                    // virtual base: stage t at + t*bb*8
                         const uint32_t off0 = sl + (uint32_t)(kStreamGroup * bb) * 8u - (uint32_t)(tlo + g.tbo) * blk_bytes; // block tb at + tb*blk_bytes
                         const bool tr = g.tbo == 0;
-                        prev = chain_sweep_call<BS>(dinv0, rhs0, off0, vb0, g.t0, g.cnt, g.dir, g.tbo, T - 1, blk_bytes, g.fwd, prev, lane,
+                        prev = chain_sweep_ool<BS>(dinv0, rhs0, off0, vb0, g.t0, g.cnt, g.dir, g.tbo, T - 1, blk_bytes, g.fwd, prev, lane,
                                                tr ? tg0 : fg0, tr ? tg1 : fg1, tr ? to0 : fo0, tr ? to1 : fo1, tr ? th0 : fh0, tr ? th1 : fh1);
                     }
                     ring_k += (uint32_t)ngroups;
