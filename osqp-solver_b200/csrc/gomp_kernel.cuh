@@ -726,21 +726,41 @@ __device__ __forceinline__ double col_dot4(uint32_t range, const double *__restr
 static __device__ __noinline__ void assemble_S(const DevSym &S, double sigma, const double *sW, const double *sA, const double *sP,
                                                double *sDinv, double *sOff, int tid, int bs) {
     const int dpb = bs * (bs + 1) / 2, ndiag = S.T * dpb, bb = bs * bs;
-    for (int e = tid; e < ndiag; e += kThreads) {
-        double acc = 0.0;
-        const uint32_t q1 = S.sd_ptr[e + 1];
-        for (uint32_t q = S.sd_ptr[e]; q < q1; ++q) {
-            const gomp::Contrib cn = S.sd_con[q];
-            acc += sW[cn.row] * sA[cn.k1] * sA[cn.k2];
+    // The contribution lists live in global memory (L2): two entries per thread are walked together so that two
+    // chains of dependent loads (pointer -> contribution -> operands) are in flight instead of one.  The order of
+    // the additions per entry is unchanged.
+    for (int e = tid; e < ndiag; e += 2 * kThreads) {
+        const int e2 = e + kThreads;
+        const bool two = e2 < ndiag;
+        const int e2c = two ? e2 : e;
+        uint32_t qa = S.sd_ptr[e], qb = S.sd_ptr[e2c];
+        const uint32_t qa1 = S.sd_ptr[e + 1], qb1 = two ? S.sd_ptr[e2c + 1] : qb;
+        const uint16_t pka = S.sd_pk[e], pkb = S.sd_pk[e2c];
+        const int kinda = S.sd_kind[e], kindb = S.sd_kind[e2c];
+        double acca = 0.0, accb = 0.0;
+        while (qa < qa1 || qb < qb1) {
+            const bool ha = qa < qa1, hb = qb < qb1;
+            const gomp::Contrib ca = S.sd_con[ha ? qa : qa1 - 1], cb = S.sd_con[hb ? qb : (ha ? qa : qb1 - 1)];
+            const double pa = sW[ca.row] * sA[ca.k1] * sA[ca.k2], pb = sW[cb.row] * sA[cb.k1] * sA[cb.k2];
+            if (ha) acca += pa;
+            if (hb) accb += pb;
+            ++qa;
+            ++qb;
         }
-        const uint16_t pk = S.sd_pk[e];
-        if (pk != 0xFFFFu) acc += sP[pk];
-        const int kind = S.sd_kind[e];
-        if (kind == 1) acc += sigma;
-        else if (kind == 2) acc = 1.0;
-        const int t = e / dpb, rc = S.tri_rc[e - t * dpb], r = rc >> 8, c = rc & 0xFF;
-        sDinv[(size_t)t * bb + r * bs + c] = acc;
-        sDinv[(size_t)t * bb + c * bs + r] = acc;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            if (w == 1 && !two) break;
+            const int ee = w ? e2 : e;
+            double acc = w ? accb : acca;
+            const uint16_t pk = w ? pkb : pka;
+            const int kind = w ? kindb : kinda;
+            if (pk != 0xFFFFu) acc += sP[pk];
+            if (kind == 1) acc += sigma;
+            else if (kind == 2) acc = 1.0;
+            const int t = ee / dpb, rc = S.tri_rc[ee - t * dpb], r = rc >> 8, c = rc & 0xFF;
+            sDinv[(size_t)t * bb + r * bs + c] = acc;
+            sDinv[(size_t)t * bb + c * bs + r] = acc;
+        }
     }
     for (int e = tid; e < S.noff; e += kThreads) {
         double acc = 0.0;
