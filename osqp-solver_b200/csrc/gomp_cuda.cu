@@ -134,6 +134,26 @@ __global__ void peak_fp64_kernel(double *out, int iters) {
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+// Work-queue order for a warm re-solve: problems in descending order of the iterations their previous solve took
+// (bucketed), so that the few long solves of a batch start first instead of forming its tail.  One CTA.
+__global__ void order_by_iters_kernel(const int *__restrict__ iters, int n, int *__restrict__ order) {
+    __shared__ int hist[257], base[257];
+    for (int k = threadIdx.x; k < 257; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    auto bucket = [](int it) { return 255 - min(255, max(0, it) >> 4); }; // long solves -> low bucket index -> front of the queue
+    for (int b = threadIdx.x; b < n; b += blockDim.x) atomicAdd(&hist[bucket(iters[b])], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int k = 0; k < 256; ++k) {
+            base[k] = acc;
+            acc += hist[k];
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < n; b += blockDim.x) order[atomicAdd(&base[bucket(iters[b])], 1)] = b;
+}
+
 __global__ void peak_smem_kernel(double *out, int iters) {
     extern __shared__ __align__(16) double buf[];
     const int words = 4096; // 32 KB of doubles per CTA
@@ -189,7 +209,8 @@ struct gomp_batch {
     // per-batch storage
     DevArray<double> d_A, d_l, d_u, d_q, d_x0, d_xs, d_zs, d_ys, d_rho, d_E, d_D, d_qs, d_dy, d_dx, d_Lg, d_Ug, d_xo, d_yo, d_pri, d_dua, d_obj;
     DevArray<unsigned long long> d_prof;
-    DevArray<int> d_status, d_iters, d_rup, d_counter, d_active;
+    DevArray<int> d_status, d_iters, d_rup, d_counter, d_active, d_order;
+    bool order_valid = false; // d_order holds the order derived from the previous solve of the same problems
     const int *active_src = nullptr; // per-QP mask of the next solves (device), NULL = all
     const double *A_src = nullptr, *l_src = nullptr, *u_src = nullptr, *q_src = nullptr; // borrowed device inputs
     long long A_pitch = 0;
@@ -361,7 +382,10 @@ int load_data(gomp_batch *h, const double *A_val, const double *l, const double 
         h->has_q = true;
     }
     CUDA_TRY(cudaEventRecord(h->evc1, h->stream));
-    if (cold) h->pending_flags = 1; // cold start; a pending warm start belongs to the previous problem
+    if (cold) {
+        h->pending_flags = 1;   // cold start; a pending warm start belongs to the previous problem
+        h->order_valid = false; // new problems: the previous iteration counts say nothing about them
+    }
     h->data_loaded = true;
     return GOMP_OK;
 }
@@ -468,7 +492,7 @@ int gomp_batch_destroy(gomp_batch *h) {
     h->d_A.release(); h->d_l.release(); h->d_u.release(); h->d_q.release(); h->d_x0.release(); h->d_xs.release();
     h->d_zs.release(); h->d_ys.release(); h->d_rho.release(); h->d_E.release(); h->d_D.release(); h->d_qs.release(); h->d_dx.release(); h->d_Lg.release(); h->d_Ug.release(); h->d_tri_rc.release(); h->d_dy.release(); h->d_xo.release();
     h->d_yo.release(); h->d_pri.release(); h->d_dua.release(); h->d_obj.release();
-    h->d_active.release(); h->d_ws.release(); h->d_row_ell.release(); h->d_col_ell.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
+    h->d_active.release(); h->d_order.release(); h->d_ws.release(); h->d_row_ell.release(); h->d_col_ell.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evc0) cudaEventDestroy(h->evc0);
@@ -687,12 +711,18 @@ int gomp_batch_solve(gomp_batch *h) {
     b.Eg = h->d_E.p; b.Dg = h->d_D.p; b.qs = h->d_qs.p; b.dyg = h->d_dy.p; b.dxg = h->d_dx.p; b.Lg = h->d_Lg.p; b.Ug = h->d_Ug.p; b.x_out = h->d_xo.p; b.y_out = h->d_yo.p;
     b.status = h->d_status.p; b.iters = h->d_iters.p; b.rho_updates = h->d_rup.p;
     b.pri_res = h->d_pri.p; b.dua_res = h->d_dua.p; b.obj_val = h->d_obj.p; b.work_counter = h->d_counter.p; b.prof = h->d_prof.p; b.active = h->active_src;
+    b.order = h->order_valid ? h->d_order.p : nullptr;
     CUDA_TRY(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     if (h->streamed) CUDA_TRY(launch_stream(h->ds, h->db, h->dst, h->dx, h->grid, h->smem_bytes, h->stream));
     else CUDA_TRY(h->kernel.launch(h->ds, h->db, h->dst, h->grid, h->smem_bytes, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
-    h->launches++;
+    // queue order of the next solve, should it be a warm re-solve of the same problems (gomp_batch_update)
+    if (!h->d_order.p) CUDA_TRY(h->d_order.alloc((size_t)h->batch));
+    order_by_iters_kernel<<<1, 1024, 0, h->stream>>>(h->d_iters.p, (int)h->batch, h->d_order.p);
+    CUDA_TRY(cudaGetLastError());
+    h->order_valid = true;
+    h->launches += 2; // the ADMM kernel and the queue-order kernel
     h->pending_flags = 0;
     return GOMP_OK;
 }

@@ -82,6 +82,7 @@ struct DevBatch {
     double *pri_res, *dua_res, *obj_val;
     int *work_counter;
     const int *active; // optional per-QP mask (NULL = all): QPs with 0 are skipped, their state and outputs stay
+    const int *order;  // optional work-queue order (NULL = by index): longest expected solves first
     unsigned long long *prof; // optional: per-phase cycle counters (thread 0 of every CTA adds), NULL = off
 };
 
@@ -957,8 +958,9 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_con
     for (;;) {
         if (tid == kSolverThreads) *sWork = atomicAdd(B.work_counter, 1);
         __syncthreads();
-        const int b = *sWork;
-        if (b >= B.batch) break;
+        const int widx = *sWork;
+        if (widx >= B.batch) break;
+        const int b = B.order != nullptr ? B.order[widx] : widx;
         if (B.active != nullptr && B.active[b] == 0) { // masked out (converged SQP problem): nothing to do
             __syncthreads();                          // everyone has read *sWork before it is overwritten
             continue;

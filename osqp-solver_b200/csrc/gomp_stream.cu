@@ -401,9 +401,10 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
     for (;;) {
         if (tid == 0) *sWork = atomicAdd(B.work_counter, 1);
         __syncthreads();
-        const int b = *sWork;
+        const int widx = *sWork;
         __syncthreads();
-        if (b >= B.batch) break;
+        if (widx >= B.batch) break;
+        const int b = B.order != nullptr ? B.order[widx] : widx;
         if (B.active != nullptr && B.active[b] == 0) continue; // masked out: state and outputs stay as they are
         const size_t bmu = (size_t)b * mu, bnp = (size_t)b * np;
         const bool hasq = B.q != nullptr;
