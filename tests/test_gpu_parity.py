@@ -327,3 +327,36 @@ def test_random_block_tridiagonal_qps(bs, T, linsys):
         if r.exit_code == 0:
             assert np.abs(got["x"][b] - r.x).max() < REL_TOL * max(1.0, np.abs(r.x).max())
             assert np.abs(got["y"][b] - r.y).max() < REL_TOL * max(1.0, np.abs(r.y).max())
+
+
+def test_active_mask_freezes_problems(env):
+    """gomp_batch_set_active: masked problems keep iterates, rho and results; the others solve as usual
+    (also exercises the longest-first queue order of the second solve)."""
+    pkg, O, pat = env
+    B = 24
+    d = pkg.problem.generate(pat, 700, B)
+    s = make_solver(pkg, pat, d)
+    s.set_warm_start(d["x0"])
+    first = s.solve(want_y=True)
+    ref = make_solver(pkg, pat, d)          # unmasked twin
+    ref.set_warm_start(d["x0"])
+    ref.solve()
+    upd = pkg.problem.relinearize(pat, 700, np.where(np.isnan(first["x"]), d["x0"], first["x"]))
+    mask = (np.arange(B) % 3 != 0).astype(np.int32)
+    s.set_active(mask)
+    s.update(upd["A_val"], upd["l"], upd["u"])
+    second = s.solve(want_y=True)
+    ref.update(upd["A_val"], upd["l"], upd["u"])
+    want = ref.solve(want_y=True)
+    off, on = mask == 0, mask == 1
+    for k in ("x", "y"):
+        np.testing.assert_array_equal(second[k][off], first[k][off])       # frozen (NaN-aware)
+        np.testing.assert_array_equal(second[k][on], want[k][on])           # same as without a mask
+    np.testing.assert_array_equal(second["iters"][off], first["iters"][off])
+    np.testing.assert_array_equal(second["iters"][on], want["iters"][on])
+    np.testing.assert_array_equal(second["exit_code"][on], want["exit_code"][on])
+    s.set_active(None)
+    third = s.solve()
+    assert (third["iters"][off] > 0).all()
+    s.close()
+    ref.close()
