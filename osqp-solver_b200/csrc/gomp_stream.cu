@@ -19,6 +19,8 @@
 //
 // Replaces the same reference calls as the resident kernel (src/osqp-wrapper.h:28,36,40,46,52); the
 // algorithm follows oracle/osqp_ref.c phase by phase (tests/cpp/emulate.cpp is its sequential model).
+#include <cstdlib>
+
 #include "gomp_stream.h"
 
 namespace gomp_dev {
@@ -31,9 +33,9 @@ constexpr int kMaxW = 4;    // off-diagonal ELL width kept in registers by the s
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int K>
+template <int K, int NT = kST>
 __device__ __forceinline__ void block_max(double (&v)[K], double *sRed, int tid) {
-    constexpr int NW = kST / 32;
+    constexpr int NW = NT / 32;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double a = v[k];
@@ -51,8 +53,9 @@ __device__ __forceinline__ void block_max(double (&v)[K], double *sRed, int tid)
     }
     __syncthreads();
 }
+template <int NT = kST>
 __device__ __forceinline__ double block_sum(double a, double *sRed, int tid) {
-    constexpr int NW = kST / 32;
+    constexpr int NW = NT / 32;
 #pragma unroll
     for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if ((tid & 31) == 0) sRed[tid >> 5] = a;
@@ -353,11 +356,12 @@ __device__ __forceinline__ Step step_of(int warp, int j, int T, int h) {
 
 } // namespace
 
-template <int BS>
-__global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_constant__ DevSym S, const __grid_constant__ DevBatch B,
+template <int BS, int NT>
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel(const __grid_constant__ DevSym S, const __grid_constant__ DevBatch B,
                                                                   const __grid_constant__ DevSettings st,
                                                                   const __grid_constant__ DevStream X) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kST = NT; // threads of this instantiation (shadows the default used by the 512-thread kernel)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bs = BS > 0 ? BS : S.bs;
     const int T = S.T, np = S.n_pad, mu = S.m_used, h = S.T / 2, bb = bs * bs;
@@ -436,7 +440,7 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
             const int rw = S.empty_rows[e];
             if (!(gl[rw] <= 0.0 && 0.0 <= gu[rw])) bad[0] = 1.0;
         }
-        block_max<1>(bad, sRed, tid); // (also: the loads above are visible to every thread)
+        block_max<1, NT>(bad, sRed, tid); // (also: the loads above are visible to every thread)
         const bool empty_infeasible = bad[0] != 0.0;
         SMARK(PH_LOAD);
 
@@ -488,8 +492,8 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                 psum += pa;
                 if (two) psum += pb;
             }
-            psum = block_sum(psum, sRed, tid);
-            block_max<1>(qn, sRed, tid);
+            psum = block_sum<NT>(psum, sRed, tid);
+            block_max<1, NT>(qn, sRed, tid);
             double ct = fmax(psum / (double)S.n, limit_scaling(qn[0]));
             ct = 1.0 / limit_scaling(ct);
             for (int k = tid; k < S.nnzPu; k += kST) gP[k] *= ct;
@@ -584,7 +588,15 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                 }
                 __syncthreads();
                 SMARK(PH_ASSEMBLE);
-                if (tid < 2 * kGroup) {
+                if (NT < 2 * kGroup) {
+                    // one factor group: the two elimination chains one after the other
+                    if (tid < kGroup) {
+#pragma unroll 1
+                        for (int t = 0; t < h; ++t) factor_block_stream<BS>(S, gDinv, gOff, sPub, sDprev, sOffBuf, true, t, t > 0 ? 1 : 0, 0, tid);
+#pragma unroll 1
+                        for (int t = T - 1; t > h; --t) factor_block_stream<BS>(S, gDinv, gOff, sPub, sDprev, sOffBuf, true, t, t < T - 1 ? 2 : 0, 0, tid);
+                    }
+                } else if (tid < 2 * kGroup) {
                     const int g = tid / kGroup, gl_ = tid - g * kGroup;
                     double *pub = sPub + g * 128, *dprev = sDprev + (size_t)g * bb, *obuf = sOffBuf + (size_t)g * bs * S.ow;
                     if (g == 0) {
@@ -853,7 +865,7 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                             na[5] = fmax(na[5], fabs(ax));
                         }
                     }
-                    block_max<6>(na, sRed, tid);
+                    block_max<6, NT>(na, sRed, tid);
                     pri_u = na[0]; pri_s = na[1]; pn_u = fmax(na[2], na[3]); pn_s = fmax(na[4], na[5]);
                 }
                 {
@@ -880,7 +892,7 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                         nb[7] = fmax(nb[7], fabs(qq));
                       }
                     }
-                    block_max<8>(nb, sRed, tid);
+                    block_max<8, NT>(nb, sRed, tid);
                     dua_u = nb[0]; dua_s = nb[1]; dn_u = fmax(nb[4], fmax(nb[3], nb[2])); dn_s = fmax(nb[7], fmax(nb[6], nb[5]));
                 }
                 pri_res = uns ? pri_u : pri_s;
@@ -934,15 +946,15 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                             nrm[0] = fmax(nrm[0], fabs(uns ? gE[i] * d : d));
                             lhs += u_ * fmax(d, 0.0) + l_ * fmin(d, 0.0);
                         }
-                        block_max<1>(nrm, sRed, tid);
-                        lhs = block_sum(lhs, sRed, tid);
+                        block_max<1, NT>(nrm, sRed, tid);
+                        lhs = block_sum<NT>(lhs, sRed, tid);
                         if (nrm[0] > kDivTol && lhs < -epi * nrm[0]) {
                             double v[1] = {0.0};
                             for (int p = tid; p < np; p += kST) {
                                 const double acc = col_dot_g(S, p, gA, gW, 0.0);
                                 v[0] = fmax(v[0], fabs(uns ? (1.0 / gD[p]) * acc : acc));
                             }
-                            block_max<1>(v, sRed, tid);
+                            block_max<1, NT>(v, sRed, tid);
                             pic = v[0] < epi * nrm[0];
                         }
                     }
@@ -958,8 +970,8 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                             nrm[0] = fmax(nrm[0], fabs(uns ? gD[p] * d : d));
                             qdx += gq[p] * d;
                         }
-                        block_max<1>(nrm, sRed, tid);
-                        qdx = block_sum(qdx, sRed, tid);
+                        block_max<1, NT>(nrm, sRed, tid);
+                        qdx = block_sum<NT>(qdx, sRed, tid);
                         const double cs_ = uns ? cscale : 1.0;
                         if (nrm[0] > kDivTol && qdx < -cs_ * edi * nrm[0]) {
                             double v[1] = {0.0};
@@ -967,7 +979,7 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                                 const double acc = pf_dot_g(S, p, gP, gdx);
                                 v[0] = fmax(v[0], fabs(uns ? (1.0 / gD[p]) * acc : acc));
                             }
-                            block_max<1>(v, sRed, tid);
+                            block_max<1, NT>(v, sRed, tid);
                             if (v[0] < cs_ * edi * nrm[0]) {
                                 double viol[1] = {0.0};
                                 for (int i = tid; i < mu; i += kST) {
@@ -977,7 +989,7 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
                                         (gLo[i] > -kInfty * kMinScaling && acc < -edi * nrm[0]))
                                         viol[0] = 1.0;
                                 }
-                                block_max<1>(viol, sRed, tid);
+                                block_max<1, NT>(viol, sRed, tid);
                                 dic = viol[0] == 0.0;
                             }
                         }
@@ -1029,16 +1041,35 @@ __global__ void __launch_bounds__(kST, 1) gomp_admm_stream_kernel(const __grid_c
     }
 }
 
+static int stream_threads() {
+    const char *e = std::getenv("GOMP_STREAM_THREADS");
+    return (e && std::atoi(e) == 256) ? 256 : 512;
+}
 cudaError_t prepare_stream(int bs, size_t smem_bytes, int *ctas_per_sm) {
-    auto fn = bs == 14 ? gomp_admm_stream_kernel<14> : gomp_admm_stream_kernel<0>;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, fn, kST, smem_bytes);
+    const int nt = stream_threads();
+    cudaError_t e;
+#define PREP(FN)                                                                                          \
+    e = cudaFuncSetAttribute(FN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);           \
+    if (e != cudaSuccess) return e;                                                                       \
+    cudaFuncSetAttribute(FN, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, FN, nt, smem_bytes);
+    if (nt == 256) {
+        if (bs == 14) { PREP((gomp_admm_stream_kernel<14, 256>)) }
+        PREP((gomp_admm_stream_kernel<0, 256>))
+    }
+    if (bs == 14) { PREP((gomp_admm_stream_kernel<14, 512>)) }
+    PREP((gomp_admm_stream_kernel<0, 512>))
+#undef PREP
 }
 cudaError_t launch_stream(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int grid, size_t smem_bytes,
                           cudaStream_t stream) {
-    if (S.bs == 14) gomp_admm_stream_kernel<14><<<grid, kST, smem_bytes, stream>>>(S, B, st, X);
-    else gomp_admm_stream_kernel<0><<<grid, kST, smem_bytes, stream>>>(S, B, st, X);
+    if (stream_threads() == 256) {
+        if (S.bs == 14) gomp_admm_stream_kernel<14, 256><<<grid, 256, smem_bytes, stream>>>(S, B, st, X);
+        else gomp_admm_stream_kernel<0, 256><<<grid, 256, smem_bytes, stream>>>(S, B, st, X);
+    } else {
+        if (S.bs == 14) gomp_admm_stream_kernel<14, 512><<<grid, 512, smem_bytes, stream>>>(S, B, st, X);
+        else gomp_admm_stream_kernel<0, 512><<<grid, 512, smem_bytes, stream>>>(S, B, st, X);
+    }
     return cudaGetLastError();
 }
 
