@@ -238,10 +238,15 @@ def run_gpu(args):
         kernel_ms.append(solver.info()["last_solve_ms"])
     kernel_avg_ms = float(np.mean(kernel_ms))
 
+    rank_ms, rank_mhz = [total_ms], [clocks.get("sm_mhz")]
     if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        # every rank's device time and median SM clock (diagnostics), then the maximum over ranks (the contract's time)
+        mine = torch.tensor([total_ms, float(clocks.get("sm_mhz") or 0.0)], dtype=torch.float64, device="cuda")
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_ms = [float(t[0].item()) for t in allr]
+        rank_mhz = [float(t[1].item()) for t in allr]
+        total_ms = max(rank_ms)
     value = world * B * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers (copies inside the timed region)
@@ -340,6 +345,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(launches),
+            "ranks": {"device_ms": [round(v, 3) for v in rank_ms], "sm_mhz": rank_mhz},
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_all, "unit": "QP/s", "cores": cores, "kind": "port", "single_core_value": cpu_1,
                              "sample": f"{sample} QPs of the same workload (problem ids {first_id}..{first_id + sample - 1}) on all {cores} host threads, "
