@@ -138,7 +138,10 @@ int gomp_batch_setup(gomp_batch *h, const double *A_val, const double *l, const 
 int gomp_batch_warm_start_x(gomp_batch *h, const double *x0);
 
 /* Run ADMM on every QP until its own termination test fires.  Iterates, rho and the
- * factorisation state persist on the device across calls. */
+ * factorisation state persist on the device across calls.  Asynchronous on the handle's stream.
+ * A solve that follows gomp_batch_update (same problems, new data) pulls the problems from the
+ * device work queue in descending order of the iterations their previous solve took, so that
+ * the longest ones start first; gomp_batch_setup (new problems) resets that order. */
 int gomp_batch_solve(gomp_batch *h);
 
 /* New A values (same pattern), bounds and/or q; each pointer may be NULL = unchanged.
