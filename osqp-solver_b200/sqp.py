@@ -112,17 +112,32 @@ def shortest_horizon(cfg, first_id, count, max_rounds=MAX_ITERATIONS, settings_f
         per_h.append(dict(code=out["exit_code"].copy(), x=out["x"].cpu().numpy(), n=pat.n))
         total += out["total_qp_solves"]
         drv.close()
-    code = np.full(count, K_UNKNOWN, dtype=np.int32)
+    code, pick = select_horizon([res["code"] for res in per_h])
     chosen = np.zeros(count, dtype=np.int32)
     xs = [None] * count
     for b in range(count):
-        for w, res in zip(horizons, per_h):
-            ec = res["code"][b]
-            if ec != K_OPTIMAL and ec != K_UNKNOWN:   # gomp-solver.h:46-47 (BatchSQP only reports these two: kept for fidelity)
-                break
-            if ec == K_OPTIMAL:                        # :48-51
-                code[b], chosen[b] = K_OPTIMAL, w
-                x = res["x"][b].copy()
-                x[res["n"] // 2:] /= cfg.time_step     # :52-54 velocities per second
-                xs[b] = x
+        if pick[b] >= 0:
+            res = per_h[pick[b]]
+            chosen[b] = horizons[pick[b]]
+            x = res["x"][b].copy()
+            x[res["n"] // 2:] /= cfg.time_step     # gomp-solver.h:52-54 velocities per second
+            xs[b] = x
     return dict(exit_code=code, waypoints=chosen, x=xs, horizons=horizons, qp_solves=total)
+
+
+def select_horizon(codes_per_horizon):
+    """The selection rule of reference src/gomp-solver.h:42-51 applied to per-horizon exit codes (longest horizon first):
+    walk the horizons, stop at the first code that is neither kOptimal nor kUnknown, remember the last kOptimal one.
+    Returns (exit_code [count], index of the chosen horizon or -1 [count])."""
+    codes = np.asarray(codes_per_horizon)
+    count = codes.shape[1]
+    out = np.full(count, K_UNKNOWN, dtype=np.int32)
+    pick = np.full(count, -1, dtype=np.int32)
+    for b in range(count):
+        for k in range(codes.shape[0]):
+            ec = codes[k, b]
+            if ec != K_OPTIMAL and ec != K_UNKNOWN:
+                break
+            if ec == K_OPTIMAL:
+                out[b], pick[b] = K_OPTIMAL, k
+    return out, pick

@@ -134,3 +134,15 @@ def test_device_relinearize_tables_reproduce_host_withObstacles(kw):
     np.testing.assert_allclose(l, want["l"], rtol=1e-13, atol=1e-13)
     np.testing.assert_allclose(u, want["u"], rtol=1e-13, atol=1e-13)
     assert (want["l"] > -1e29).sum() > (d["l"] > -1e29).sum() or (want["l"] != d["l"]).any()
+
+
+def test_horizon_selection_rule():
+    """reference src/gomp-solver.h:42-51: last kOptimal horizon before the first failed QP; kUnknown does not stop the walk."""
+    pkg = package()
+    codes = [[0, 0, 10, 1, 10],    # longest horizon
+             [0, 10, 0, 0, 10],
+             [0, 1, 0, 0, 10],
+             [6, 0, 10, 0, 10]]    # shortest
+    out, pick = pkg.sqp.select_horizon(codes)
+    assert out.tolist() == [0, 0, 0, 10, 10]
+    assert pick.tolist() == [2, 0, 2, -1, -1]
