@@ -42,6 +42,12 @@ constexpr int kThreads = 512;              // 16 warps
 constexpr int kSolverThreads = 64;         // warps 0, 1
 constexpr int kOwners = kThreads - kSolverThreads; // 448 row / variable owners
 constexpr int kRedK = 14;                  // widest multi-value block reduction
+// On-device phase timers (GOMP_PROFILE_PHASES at run time) are compiled in only with -DGOMP_PHASE_TIMERS=1
+// (make PROFILE=1): they keep a 64-bit time stamp alive through the whole solve, which the 128-register budget feels.
+#ifndef GOMP_PHASE_TIMERS
+#define GOMP_PHASE_TIMERS 0
+#endif
+constexpr bool kTimers = GOMP_PHASE_TIMERS != 0;
 
 // ---- device-side views ------------------------------------------------------------------------
 struct DevSym {
@@ -318,7 +324,7 @@ __device__ __forceinline__ double chain_step(const SolverCtx &C, int t, int tb, 
 enum { PH_LOAD = 0, PH_SCALE, PH_FACTOR, PH_RHS, PH_SOLVE, PH_UPDATE, PH_INFO, PH_STORE, PH_ASSEMBLE, PH_CHAIN, PH_COUNT };
 #define PHASE_MARK(ph)                                                              \
     do {                                                                            \
-        if (B.prof != nullptr && tid == kSolverThreads) {                           \
+        if (kTimers && B.prof != nullptr && tid == kSolverThreads) {                           \
             const long long now__ = clock64();                                      \
             atomicAdd(&B.prof[ph], (unsigned long long)(now__ - t_phase));          \
             t_phase = now__;                                                        \
@@ -847,9 +853,9 @@ static __device__ __noinline__ void solver_role(const DevSym &S, double sigma, u
                 const double u = chain_sweep<BS>(dinv0, rhs0, off0, vb0, 0, h, +1, -1, T - 1, blk_bytes, true, 0.0, lane, fg0, fg1, fo0, fo1, fh0, fh1);
                 (void)u;
                 __syncwarp();
-                if (prof != nullptr && tid == 0) atomicAdd(&prof[10], (unsigned long long)(clock64() - t_chain0));
+                if (kTimers && prof != nullptr && tid == 0) atomicAdd(&prof[10], (unsigned long long)(clock64() - t_chain0));
                 named_bar_sync(1, 64);
-                if (prof != nullptr && tid == 0) atomicAdd(&prof[11], (unsigned long long)(clock64() - t_chain0));
+                if (kTimers && prof != nullptr && tid == 0) atomicAdd(&prof[11], (unsigned long long)(clock64() - t_chain0));
                 double yv = lane < bs ? sRHS[h * bs + lane] : 0.0;
                 if (lane < bs) {
                     if (h > 0) yv -= off_mul(C, h - 1, sRHS + (h - 1) * bs, lane);
@@ -858,7 +864,7 @@ static __device__ __noinline__ void solver_role(const DevSym &S, double sigma, u
                 const double xm = apply_dinv<BS>(C, h, yv, lane);
                 if (lane < bs) sRHS[h * bs + lane] = xm;
                 named_bar_sync(2, 64);
-                if (prof != nullptr && tid == 0) atomicAdd(&prof[12], (unsigned long long)(clock64() - t_chain0));
+                if (kTimers && prof != nullptr && tid == 0) atomicAdd(&prof[12], (unsigned long long)(clock64() - t_chain0));
                 const double xm2 = sRHS[h * bs + rl]; // both lanes of a row hold the middle stage's value
                 chain_sweep<BS>(dinv0, rhs0, off0, vb0, h - 1, h, -1, 0, T - 1, blk_bytes, false, xm2, lane, tg0, tg1, to0, to1, th0, th1);
             } else { // stages T-1 .. h+1 forward (Off_t' u_{t+1}), then back down (Off_{t-1} x_{t-1})
@@ -910,7 +916,7 @@ static __device__ __noinline__ void solver_role(const DevSym &S, double sigma, u
                 __syncwarp();
             }
         }
-        if (prof != nullptr && tid == 0) atomicAdd(&prof[PH_CHAIN], (unsigned long long)(clock64() - t_chain0));
+        if (kTimers && prof != nullptr && tid == 0) atomicAdd(&prof[PH_CHAIN], (unsigned long long)(clock64() - t_chain0));
         __syncthreads(); // (F) x~ ready
     }
 }
@@ -1218,7 +1224,7 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_con
                 long long t_info = clock64();
 #define INFO_MARK(slot)                                                              \
     do {                                                                             \
-        if (B.prof != nullptr && tid == kSolverThreads) {                            \
+        if (kTimers && B.prof != nullptr && tid == kSolverThreads) {                            \
             const long long now__ = clock64();                                       \
             atomicAdd(&B.prof[slot], (unsigned long long)(now__ - t_info));          \
             t_info = now__;                                                          \

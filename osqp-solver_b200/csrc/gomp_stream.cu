@@ -347,7 +347,7 @@ __device__ __forceinline__ Step step_of(int warp, int j, int T, int h) {
 
 #define SMARK(ph)                                                                   \
     do {                                                                            \
-        if (B.prof != nullptr && tid == 0) {                                        \
+        if (kTimers && B.prof != nullptr && tid == 0) {                                        \
             const long long now__ = clock64();                                      \
             atomicAdd(&B.prof[ph], (unsigned long long)(now__ - t_phase));          \
             t_phase = now__;                                                        \
@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                     ring_k += (uint32_t)nsteps;
                 }
             }
-            if (B.prof != nullptr && tid == 0) atomicAdd(&B.prof[PH_CHAIN], (unsigned long long)(clock64() - t_phase));
+            if (kTimers && B.prof != nullptr && tid == 0) atomicAdd(&B.prof[PH_CHAIN], (unsigned long long)(clock64() - t_phase));
             __syncthreads();
             SMARK(PH_SOLVE);
 

@@ -1,6 +1,7 @@
 """BASELINE.json configs[3]: long-horizon GOMP QPs (default N = 7, H = 400) on the streamed back end, timed
 beside the CPU oracle on the same inputs.
-usage: python tools/long_horizon.py [waypoints] [batch ...]        (prints one JSON line per batch size)"""
+usage: python tools/long_horizon.py [waypoints] [batch ...]        (prints one JSON line per batch size)
+Phase breakdown: build with `make -C osqp-solver_b200 PROFILE=1` and run with GOMP_PROFILE_PHASES=1."""
 import json
 import os
 import sys

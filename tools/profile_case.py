@@ -1,5 +1,7 @@
 """Small fixed case for ncu: a few waves of the 7-DoF H=50 workload through the CUDA hot path.
-usage: python tools/profile_case.py [batch] [repeats]"""
+usage: python tools/profile_case.py [batch] [repeats]
+Phase breakdown: build with `make -C osqp-solver_b200 PROFILE=1` (compiles the on-device timers in) and run with
+GOMP_PROFILE_PHASES=1; the production build prints the kernel time only."""
 import os
 import sys
 
