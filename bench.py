@@ -167,7 +167,8 @@ def run_gpu(args):
     main = torch.cuda.current_stream()
 
     def make(borrow, stream):
-        st = S.default_settings(borrow_inputs=1 if borrow else 0, stream=stream.cuda_stream, device=local_rank)
+        st = S.default_settings(borrow_inputs=1 if borrow else 0, stream=stream.cuda_stream, device=local_rank,
+                                linsys=int(os.environ.get("GOMP_BENCH_LINSYS", "0")))  # 0 = AUTO (the measured configuration)
         return S.BatchQPSolver(pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx,
                                batch=B, settings=st, var_order=pat.var_order, block_size=pat.block_size)
 

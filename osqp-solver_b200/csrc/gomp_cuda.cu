@@ -579,23 +579,51 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
             return (int)at;
         };
         x.slot_doubles = s.bs * s.bs + s.bs * s.ow;
-        x.oRHS = take(8 * (size_t)s.n_pad);
         // the grouped ring (fast path of gomp_stream.cu: compile-time block size 14, uniform 2-wide off-diagonal pattern)
-        // needs kStreamGroup * kStreamGroupRing stage slots per warp, the generic path kStreamRing
+        // needs grp * grp_ring stage slots per warp, the generic path kStreamRing
         const bool grouped = s.bs == 14 && h->ds.uniform_off && s.ow <= 2 && s.owT <= 2;
-        x.ring_doubles = (grouped ? std::max(kStreamRing, kStreamGroup * kStreamGroupRing) : kStreamRing) * x.slot_doubles;
-        x.oRing = take(8 * (size_t)2 * x.ring_doubles);
-        x.oPub = take(8 * 256);
-        x.oDprev = take(8 * (size_t)2 * s.bs * s.bs);
-        x.oOffBuf = take(8 * (size_t)2 * s.bs * std::max(1, s.ow));
-        x.oV = take(8 * 128);
-        x.oRed = take(8 * (size_t)kRedK * (kStreamThreads / 32));
-        x.oBar = take(8 * 2 * kStreamRing + 16);
-        h->smem_bytes = o;
+        auto layout = [&](bool small) {
+            o = 0;
+            x.small = small ? 1 : 0;
+            x.grp = small ? kStreamSmallGroup : kStreamGroup;
+            x.grp_ring = small ? kStreamSmallGroupRing : kStreamGroupRing;
+            x.oRHS = take(8 * (size_t)s.n_pad);
+            // generic path: as many one-stage slots as fit beside the fixed regions (at least 3, at most kStreamRing)
+            x.gen_ring = kStreamRing;
+            if (!grouped) {
+                const size_t fixed = 8 * (size_t)s.n_pad + 8 * ((size_t)3 * s.bs * s.bs + (size_t)4 * s.bs * std::max(1, s.ow)) + 8192;
+                const size_t room = (size_t)prop.sharedMemPerBlockOptin > fixed ? (size_t)prop.sharedMemPerBlockOptin - fixed : 0;
+                x.gen_ring = (int)std::max<size_t>(3, std::min<size_t>(kStreamRing, room / (2 * 8 * (size_t)x.slot_doubles)));
+            }
+            x.ring_doubles = (grouped ? std::max(small ? 0 : kStreamRing, x.grp * x.grp_ring) : x.gen_ring) * x.slot_doubles;
+            x.oRing = take(8 * (size_t)2 * x.ring_doubles);
+            const int groups = 2; // factor groups: 2 x 224 threads, or 2 x 112 in the 256-thread CTAs of the small-QP mode
+            x.oPub = take(8 * (size_t)128 * groups);
+            x.oDprev = take(8 * (size_t)groups * s.bs * s.bs);
+            x.oOffBuf = take(8 * (size_t)groups * s.bs * std::max(1, s.ow));
+            x.oV = take(8 * 128);
+            x.oMid = take(8 * ((size_t)s.bs * s.bs + 2 * (size_t)s.bs * std::max(1, s.ow)));
+            x.oRed = take(8 * (size_t)kRedK * ((small ? kStreamSmallThreads : kStreamThreads) / 32));
+            x.oBar = take(8 * 4 * kStreamRing + 16); // full + empty barriers of both chains, work-queue slot
+            x.oA = x.oW = x.oRowEnt = x.oRowRange = x.oColRange = x.oCscRow = 0;
+            if (small) {
+                x.oA = take(8 * (size_t)s.nnzA);
+                x.oW = take(8 * (size_t)std::max(1, s.m_used));
+                x.oRowEnt = take(4 * ((size_t)s.nnzA + 4));
+                x.oRowRange = take(2 * ((size_t)s.m_used + 2)); // 16-bit CSR row pointers
+                x.oColRange = take(4 * (size_t)s.n_pad);
+                x.oCscRow = take(2 * ((size_t)s.nnzA + 4));
+            }
+            return o;
+        };
+        // small-QP mode: two 256-thread CTAs per SM, sparse data in shared memory -- when a CTA fits half an SM
+        const size_t half_sm = (size_t)prop.sharedMemPerMultiprocessor / 2 - 1024;
+        bool small = grouped && !std::getenv("GOMP_STREAM_NO_SMALL") && layout(true) <= half_sm;
+        h->smem_bytes = layout(small);
         if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
             return bail(fail(GOMP_ERR_UNSUPPORTED, "right-hand side of the block solve does not fit in shared memory (" +
                                                        std::to_string(h->smem_bytes) + " bytes needed)"));
-        cudaError_t e = prepare_stream(s.bs, h->smem_bytes, &occ);
+        cudaError_t e = prepare_stream(s.bs, small, h->smem_bytes, &occ);
         if (e != cudaSuccess) return bail(fail(GOMP_ERR_CUDA, std::string("kernel preparation failed: ") + cudaGetErrorString(e)));
         if (occ < 1) return bail(fail(GOMP_ERR_CUDA, "kernel cannot be resident (occupancy 0)"));
         long long w = 0;
@@ -849,7 +877,7 @@ int gomp_batch_info(gomp_batch *h, gomp_info *info) {
     const gomp::Symbolic &s = h->sym;
     info->batch = h->batch; info->n = s.n; info->m = s.m; info->m_used = s.m_used; info->nnzA = s.nnzA; info->nnzP = s.nnzPu;
     info->block_size = s.bs; info->num_blocks = s.T; info->offdiag_width = s.ow;
-    info->linsys = h->streamed ? GOMP_LINSYS_BLOCKTRI_GLOBAL : GOMP_LINSYS_BLOCKTRI_SMEM; info->threads_per_cta = h->streamed ? kStreamThreads : kThreads; info->ctas_per_sm = h->ctas_per_sm;
+    info->linsys = h->streamed ? GOMP_LINSYS_BLOCKTRI_GLOBAL : GOMP_LINSYS_BLOCKTRI_SMEM; info->threads_per_cta = h->streamed ? (h->dx.small ? kStreamSmallThreads : kStreamThreads) : kThreads; info->ctas_per_sm = h->ctas_per_sm;
     info->num_sms = h->num_sms; info->grid = h->grid; info->smem_bytes = (int64_t)h->smem_bytes;
     info->workspace_bytes = (int64_t)h->workspace_bytes; info->kernel_launches = h->launches;
     float ms = 0;

@@ -199,17 +199,19 @@ __device__ __forceinline__ void col_scale2(const DevSym &S, const DevStream &X, 
 // `dprev` (shared memory, bs*bs doubles per group) carries the inverse of the previous stage of the chain to the
 // next call, so the Schur update never waits on the global copy just written.
 // `offbuf` (shared memory, bs*ow doubles per group) stages the off-diagonal block of the Schur update.
-template <int BS>
+// GS = threads of the group (224: one matrix entry per thread for a 14 x 14 block; 128: up to two -- the 256-thread CTAs
+// of the small-QP mode run both elimination chains at once with two half-size groups).
+template <int BS, int GS>
 __device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dall, const double *Offall, double *pub, double *dprev,
                                                     double *offbuf, bool prev_valid, int t, int mode, int g, int gl) {
-    constexpr int EPL = BS > 0 ? (BS * BS + kGroup - 1) / kGroup : 5; // entries per thread (bs <= 32)
+    constexpr int EPL = BS > 0 ? (BS * BS + GS - 1) / GS : (1024 + GS - 1) / GS; // entries per thread (bs <= 32)
     const int bs = BS > 0 ? BS : S.bs, nn = bs * bs;
     double *M = Dall + (size_t)t * nn;
     double val[EPL];
     int ri[EPL], ci[EPL];
 #pragma unroll
     for (int q = 0; q < EPL; ++q) {
-        const int e = gl + q * kGroup;
+        const int e = gl + q * GS;
         ri[q] = e < nn ? e / bs : -1;
         ci[q] = e < nn ? e - ri[q] * bs : -1;
         val[q] = e < nn ? M[e] : 0.0;
@@ -221,9 +223,9 @@ __device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dal
         const int tb = above ? t - 1 : t;
         const double *Dn = prev_valid ? dprev : Dall + (size_t)(above ? t - 1 : t + 1) * nn;
         const double *gblk = Offall + (size_t)tb * bs * S.ow;
-        if (pass == 2 && (mode & 1)) named_bar_sync(4 + g, kGroup); // middle stage: the first pass is done with offbuf
-        for (int e = gl; e < bs * S.ow; e += kGroup) offbuf[e] = gblk[e];
-        named_bar_sync(4 + g, kGroup);
+        if (pass == 2 && (mode & 1)) named_bar_sync(4 + g, GS); // middle stage: the first pass is done with offbuf
+        for (int e = gl; e < bs * S.ow; e += GS) offbuf[e] = gblk[e];
+        named_bar_sync(4 + g, GS);
         const double *blk = offbuf;
         const int tp = S.uniform_off ? 0 : tb; // pattern block (L1-resident when every block shares one pattern)
         const int cnt = above ? S.ow : S.owT;
@@ -259,40 +261,46 @@ __device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dal
             val[q] -= acc;
         }
     }
-    if (BS > 0 && BS <= 16 && BS % 2 == 0 && EPL == 1) {
+    if (BS > 0 && BS <= 16 && BS % 2 == 0 && EPL <= 2) {
         // Gauss-Jordan sweeps with 2x2 pivot blocks, as in the resident kernel (gomp_kernel.cuh, factor_block_group)
-        const int i = ri[0], j = ci[0];
-        double v = val[0];
 #pragma unroll 1
         for (int k = 0; k < BS; k += 2) {
             double *buf = pub + ((k >> 1) & 1) * 64; // [row k | row k+1 | column k | column k+1], 16 doubles each
-            if (i >= 0) {
-                if (i == k) buf[j] = v;
-                if (i == k + 1) buf[16 + j] = v;
-                if (j == k) buf[32 + i] = v;
-                if (j == k + 1) buf[48 + i] = v;
+#pragma unroll
+            for (int q = 0; q < EPL; ++q) {
+                const int i = ri[q], j = ci[q];
+                if (i < 0) continue;
+                if (i == k) buf[j] = val[q];
+                if (i == k + 1) buf[16 + j] = val[q];
+                if (j == k) buf[32 + i] = val[q];
+                if (j == k + 1) buf[48 + i] = val[q];
             }
-            named_bar_sync(4 + g, kGroup);
-            if (i < 0) continue;
+            named_bar_sync(4 + g, GS);
             const double a = buf[k], b = buf[k + 1], c = buf[16 + k], d = buf[16 + k + 1];
-            const double r1 = buf[j], r2 = buf[16 + j];
-            const double c1 = buf[32 + i], c2 = buf[48 + i];
             const double invdet = 1.0 / (a * d - b * c);
-            const bool ik = (i >> 1) == (k >> 1), jk = (j >> 1) == (k >> 1);
-            const double u1 = d * r1 - b * r2, u2 = a * r2 - c * r1;
-            if (!ik && !jk) {
-                v = fma(-(c1 * u1 + c2 * u2), invdet, v);
-            } else if (ik && !jk) {
-                v = (i == k ? u1 : u2) * invdet;
-            } else if (!ik && jk) {
-                const double w1 = c1 * d - c2 * c, w2 = c2 * a - c1 * b;
-                v = -((j == k ? w1 : w2) * invdet);
-            } else {
-                const double adj = i == k ? (j == k ? d : -b) : (j == k ? -c : a);
-                v = adj * invdet;
+#pragma unroll
+            for (int q = 0; q < EPL; ++q) {
+                const int i = ri[q], j = ci[q];
+                if (i < 0) continue;
+                const double r1 = buf[j], r2 = buf[16 + j];
+                const double c1 = buf[32 + i], c2 = buf[48 + i];
+                const bool ik = (i >> 1) == (k >> 1), jk = (j >> 1) == (k >> 1);
+                const double u1 = d * r1 - b * r2, u2 = a * r2 - c * r1;
+                double v = val[q];
+                if (!ik && !jk) {
+                    v = fma(-(c1 * u1 + c2 * u2), invdet, v);
+                } else if (ik && !jk) {
+                    v = (i == k ? u1 : u2) * invdet;
+                } else if (!ik && jk) {
+                    const double w1 = c1 * d - c2 * c, w2 = c2 * a - c1 * b;
+                    v = -((j == k ? w1 : w2) * invdet);
+                } else {
+                    const double adj = i == k ? (j == k ? d : -b) : (j == k ? -c : a);
+                    v = adj * invdet;
+                }
+                val[q] = v;
             }
         }
-        val[0] = v;
     } else
 #pragma unroll 1
     for (int k = 0; k < bs; ++k) { // Gauss-Jordan without pivoting (SPD block)
@@ -302,7 +310,7 @@ __device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dal
             if (ri[q] == k) rowk[ci[q]] = val[q];
             if (ci[q] == k) colk[ri[q]] = val[q];
         }
-        named_bar_sync(4 + g, kGroup);
+        named_bar_sync(4 + g, GS);
         const double pinv = 1.0 / rowk[k];
 #pragma unroll
         for (int q = 0; q < EPL; ++q) {
@@ -314,14 +322,14 @@ __device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dal
             else val[q] = pinv;
         }
     }
-    named_bar_sync(4 + g, kGroup); // every thread is done reading dprev (Schur update) and the last pivot row / column
+    named_bar_sync(4 + g, GS); // every thread is done reading dprev (Schur update) and the last pivot row / column
 #pragma unroll
     for (int q = 0; q < EPL; ++q)
         if (ri[q] >= 0) {
-            M[gl + q * kGroup] = val[q];
-            dprev[gl + q * kGroup] = val[q];
+            M[gl + q * GS] = val[q];
+            dprev[gl + q * GS] = val[q];
         }
-    named_bar_sync(4 + g, kGroup); // the next stage of this chain reads the inverse just stored
+    named_bar_sync(4 + g, GS); // the next stage of this chain reads the inverse just stored
 }
 
 // ---- block substitution: the step list of one chain warp ------------------------------------------------------
@@ -356,7 +364,11 @@ __device__ __forceinline__ Step step_of(int warp, int j, int T, int h) {
 
 } // namespace
 
-template <int BS, int NT>
+// SM ("small QP"): the QP's A values, w = rho z - y and the CSR / CSC pattern arrays are kept in shared memory as in
+// the resident kernel (the sparse phases then run against shared memory instead of L2); iterates, bounds, scaling
+// vectors and the factor stay in the global workspace.  With 256 threads such a CTA needs < 113 KB for the N=7, H=50
+// shape, so two of them share an SM: one QP's substitution chain overlaps the other's sparse phases.
+template <int BS, int NT, bool SM>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel(const __grid_constant__ DevSym S, const __grid_constant__ DevBatch B,
                                                                   const __grid_constant__ DevSettings st,
                                                                   const __grid_constant__ DevStream X) {
@@ -371,18 +383,41 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
     double *const sDprev = reinterpret_cast<double *>(smem_raw + X.oDprev); // [2][bs*bs]
     double *const sOffBuf = reinterpret_cast<double *>(smem_raw + X.oOffBuf); // [2][bs*ow]
     double *const sV = reinterpret_cast<double *>(smem_raw + X.oV);
+    double *const sMid = reinterpret_cast<double *>(smem_raw + X.oMid); // middle stage: [inverse | Off_{h-1} | Off_h], refreshed per factorisation
     double *const sRed = reinterpret_cast<double *>(smem_raw + X.oRed);
-    uint64_t *const sFull = reinterpret_cast<uint64_t *>(smem_raw + X.oBar); // [2][kRing]
-    int *const sWork = reinterpret_cast<int *>(smem_raw + X.oBar + 8 * 2 * kStreamRing);
+    uint64_t *const sFull = reinterpret_cast<uint64_t *>(smem_raw + X.oBar); // [2][kStreamRing] "slot filled" (bulk copies complete)
+    uint64_t *const sEmpty = sFull + 2 * kStreamRing;                        // [2][kStreamRing] "slot consumed" (fast path)
+    int *const sWork = reinterpret_cast<int *>(smem_raw + X.oBar + 8 * 4 * kStreamRing);
 
     // per-CTA workspace (global, L2-resident)
     double *const ws = X.ws + (size_t)blockIdx.x * X.stride;
-    double *const gA = ws + X.wA, *const gP = ws + X.wP, *const gW = ws + X.wW, *const gRho = ws + X.wRho, *const gDinv = ws + X.wDinv,
+    double *const gA = SM ? reinterpret_cast<double *>(smem_raw + X.oA) : ws + X.wA;
+    double *const gW = SM ? reinterpret_cast<double *>(smem_raw + X.oW) : ws + X.wW;
+    double *const gP = ws + X.wP, *const gRho = ws + X.wRho, *const gDinv = ws + X.wDinv,
                  *const gOff = ws + X.wOff, *const gT = ws + X.wT, *const gLo = ws + X.wLo, *const gHi = ws + X.wHi;
 
-    if (tid == 0) {
-        for (int k = 0; k < 2 * kStreamRing; ++k) mbar_init(sFull + k, 1);
+    // small-QP mode: pattern arrays in shared memory, staged once per kernel
+    uint32_t *const sRowEnt = reinterpret_cast<uint32_t *>(smem_raw + X.oRowEnt), *const sColRange = reinterpret_cast<uint32_t *>(smem_raw + X.oColRange);
+    uint16_t *const sCscRow = reinterpret_cast<uint16_t *>(smem_raw + X.oCscRow), *const sRowPtr = reinterpret_cast<uint16_t *>(smem_raw + X.oRowRange);
+    // (first entry << 8 | length) of compact row i, from the 16-bit CSR pointers
+    auto row_range = [&](int i) { const uint32_t a = sRowPtr[i]; return (a << 8) | ((uint32_t)sRowPtr[i + 1] - a); };
+    if (SM) {
+        for (int k = tid; k < S.nnzA; k += kST) {
+            sRowEnt[k] = S.row_csr[k];
+            sCscRow[k] = S.csc_row[k];
+        }
+        if (tid < 4) {
+            sRowEnt[S.nnzA + tid] = 0u; // the 4-wide entry loops may read past the last row
+            sCscRow[S.nnzA + tid] = 0;
+        }
+        for (int k = tid; k < np; k += kST) sColRange[k] = S.col_range[k];
+        for (int k = tid; k <= mu; k += kST) sRowPtr[k] = S.row_ptr[k];
     }
+    if (tid == 0) {
+        for (int k = 0; k < 4 * kStreamRing; ++k) mbar_init(sFull + k, 1);
+    }
+    uint32_t prod_k0 = 0, prod_k1 = 0; // producer warp: groups of completed solves, top / bottom chain
+    int pre = 0;                        // producer lane: groups already issued for the coming solve
     uint32_t ring_k = 0; // slots this warp has consumed since the kernel started (slot = ring_k % kRing, parity from ring_k / kRing)
     __syncthreads();
 
@@ -401,6 +436,80 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
         ub[q] = (upat && q < S.owT) ? S.offT_row[r * S.owT + q] : -1;
         us[q] = (upat && q < S.owT) ? S.offT_slot[r * S.owT + q] : 0;
     }
+
+    // sparse products / norms / scalings on two rows or columns, on whichever copy of the pattern this mode uses
+    auto row_dot2 = [&](int i1, int i2, const double *vec, double &r1, double &r2) {
+        if (SM) {
+            r1 = row_dot4(sRowEnt, row_range(i1), gA, vec);
+            r2 = row_dot4(sRowEnt, row_range(i2), gA, vec);
+        } else {
+            row_dot_ell2(X, mu, i1, i2, gA, vec, r1, r2);
+        }
+    };
+    auto row_absmax2 = [&](int i1, int i2, double &r1, double &r2) {
+        if (SM) {
+            double a[2] = {0.0, 0.0};
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const uint32_t rg = row_range(w ? i2 : i1);
+                for (int q = (int)(rg >> 8), q1 = q + (int)(rg & 0xFFu); q < q1; ++q) a[w] = fmax(a[w], fabs(gA[sRowEnt[q] & 0xFFFFu]));
+            }
+            r1 = a[0];
+            r2 = a[1];
+        } else {
+            row_absmax_ell2(X, mu, i1, i2, gA, r1, r2);
+        }
+    };
+    auto row_scale2 = [&](int i1, int i2, bool two, double s1, double s2) {
+        if (SM) {
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                if (w == 1 && !two) break;
+                const uint32_t rg = row_range(w ? i2 : i1);
+                const double sc = w ? s2 : s1;
+                for (int q = (int)(rg >> 8), q1 = q + (int)(rg & 0xFFu); q < q1; ++q) gA[sRowEnt[q] & 0xFFFFu] *= sc;
+            }
+        } else {
+            row_scale_ell2(X, mu, i1, i2, two, gA, s1, s2);
+        }
+    };
+    auto col_dot2 = [&](int p1, int p2, const double *vec, double &r1, double &r2) {
+        if (SM) {
+            r1 = col_dot4(sColRange[p1], gA, sCscRow, vec, r1);
+            r2 = col_dot4(sColRange[p2], gA, sCscRow, vec, r2);
+        } else {
+            col_dot_ell2(S, X, np, p1, p2, gA, vec, r1, r2);
+        }
+    };
+    auto col_absmax_2 = [&](int p1, int p2, double &r1, double &r2) {
+        if (SM) {
+            double a[2] = {0.0, 0.0};
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const uint32_t rg = sColRange[w ? p2 : p1];
+                for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) a[w] = fmax(a[w], fabs(gA[k]));
+            }
+            r1 = a[0];
+            r2 = a[1];
+        } else {
+            col_absmax2(S, X, p1, p2, gA, r1, r2);
+        }
+    };
+    auto col_scale_2 = [&](int p1, int p2, bool two, double s1, double s2) {
+        if (SM) {
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                if (w == 1 && !two) break;
+                const uint32_t rg = sColRange[w ? p2 : p1];
+                const double sc = w ? s2 : s1;
+                for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) gA[k] *= sc;
+            }
+        } else {
+            col_scale2(S, X, p1, p2, two, gA, s1, s2);
+        }
+    };
+    auto row_dot1 = [&](int i, const double *vec) { return SM ? row_dot4(sRowEnt, row_range(i), gA, vec) : row_dot_g(S, i, gA, vec); };
+    auto col_dot1 = [&](int p_, const double *vec) { return SM ? col_dot4(sColRange[p_], gA, sCscRow, vec, 0.0) : col_dot_g(S, p_, gA, vec, 0.0); };
 
     for (;;) {
         if (tid == 0) *sWork = atomicAdd(B.work_counter, 1);
@@ -450,21 +559,21 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
         for (int it = 0; it < st.scaling; ++it) {
             COLS2(p, p2, two) {
                 double na, nb;
-                col_absmax2(S, X, p, p2, gA, na, nb);
+                col_absmax_2(p, p2, na, nb);
                 const double pa = pf_absmax_g(S, p, gP), pb = pf_absmax_g(S, p2, gP);
                 gT[p] = 1.0 / sqrt(limit_scaling(fmax(pa, na)));
                 if (two) gT[p2] = 1.0 / sqrt(limit_scaling(fmax(pb, nb)));
             }
             ROWS2(i, i2, two) {
                 double na, nb;
-                row_absmax_ell2(X, mu, i, i2, gA, na, nb);
+                row_absmax2(i, i2, na, nb);
                 gW[i] = 1.0 / sqrt(limit_scaling(na));
                 if (two) gW[i2] = 1.0 / sqrt(limit_scaling(nb));
             }
             __syncthreads();
             ROWS2(i, i2, two) {
                 const double ea = gW[i], eb = gW[i2];
-                row_scale_ell2(X, mu, i, i2, two, gA, ea, eb);
+                row_scale2(i, i2, two, ea, eb);
                 gE[i] *= ea;
                 if (two) gE[i2] *= eb;
             }
@@ -477,7 +586,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             double psum = 0.0, qn[1] = {0.0};
             COLS2(p, p2, two) {
                 const double da = gT[p], db = gT[p2];
-                col_scale2(S, X, p, p2, two, gA, da, db);
+                col_scale_2(p, p2, two, da, db);
                 gD[p] *= da;
                 if (two) gD[p2] *= db;
                 if (hasq) {
@@ -531,7 +640,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             __syncthreads();
             ROWS2(i, i2, two) {
                 double za, zb;
-                row_dot_ell2(X, mu, i, i2, gA, gx, za, zb);
+                row_dot2(i, i2, gx, za, zb);
                 gz[i] = za;
                 if (two) gz[i2] = zb;
             }
@@ -589,28 +698,43 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                 __syncthreads();
                 SMARK(PH_ASSEMBLE);
                 if (NT < 2 * kGroup) {
-                    // one factor group: the two elimination chains one after the other
-                    if (tid < kGroup) {
+                    // 256-thread CTA: two half-size groups (two matrix entries per thread), one per elimination chain
+                    constexpr int kHalf = 128; // four warps per chain (named barriers count whole warps)
+                    if (tid < 2 * kHalf) {
+                        const int g = tid / kHalf, gl_ = tid - g * kHalf;
+                        double *pub = sPub + g * 128, *dprev = sDprev + (size_t)g * bb, *obuf = sOffBuf + (size_t)g * bs * S.ow;
+                        if (g == 0) {
 #pragma unroll 1
-                        for (int t = 0; t < h; ++t) factor_block_stream<BS>(S, gDinv, gOff, sPub, sDprev, sOffBuf, true, t, t > 0 ? 1 : 0, 0, tid);
+                            for (int t = 0; t < h; ++t) factor_block_stream<BS, kHalf>(S, gDinv, gOff, pub, dprev, obuf, true, t, t > 0 ? 1 : 0, 0, gl_);
+                        } else {
 #pragma unroll 1
-                        for (int t = T - 1; t > h; --t) factor_block_stream<BS>(S, gDinv, gOff, sPub, sDprev, sOffBuf, true, t, t < T - 1 ? 2 : 0, 0, tid);
+                            for (int t = T - 1; t > h; --t) factor_block_stream<BS, kHalf>(S, gDinv, gOff, pub, dprev, obuf, true, t, t < T - 1 ? 2 : 0, 1, gl_);
+                        }
                     }
                 } else if (tid < 2 * kGroup) {
                     const int g = tid / kGroup, gl_ = tid - g * kGroup;
                     double *pub = sPub + g * 128, *dprev = sDprev + (size_t)g * bb, *obuf = sOffBuf + (size_t)g * bs * S.ow;
                     if (g == 0) {
 #pragma unroll 1
-                        for (int t = 0; t < h; ++t) factor_block_stream<BS>(S, gDinv, gOff, pub, dprev, obuf, true, t, t > 0 ? 1 : 0, 0, gl_);
+                        for (int t = 0; t < h; ++t) factor_block_stream<BS, kGroup>(S, gDinv, gOff, pub, dprev, obuf, true, t, t > 0 ? 1 : 0, 0, gl_);
                     } else {
 #pragma unroll 1
-                        for (int t = T - 1; t > h; --t) factor_block_stream<BS>(S, gDinv, gOff, pub, dprev, obuf, true, t, t < T - 1 ? 2 : 0, 1, gl_);
+                        for (int t = T - 1; t > h; --t) factor_block_stream<BS, kGroup>(S, gDinv, gOff, pub, dprev, obuf, true, t, t < T - 1 ? 2 : 0, 1, gl_);
                     }
                 }
                 __syncthreads();
                 // the middle stage takes both neighbours' inverses from the global copies
-                if (tid < kGroup) factor_block_stream<BS>(S, gDinv, gOff, sPub, sDprev, sOffBuf, false, h, (h > 0 ? 1 : 0) | (h < T - 1 ? 2 : 0), 0, tid);
+                if (tid < kGroup) factor_block_stream<BS, kGroup>(S, gDinv, gOff, sPub, sDprev, sOffBuf, false, h, (h > 0 ? 1 : 0) | (h < T - 1 ? 2 : 0), 0, tid);
                 fence_proxy_async_all(); // the factor is read by bulk copies (async proxy) from here on
+                __syncthreads();
+                {   // the middle stage's operands stay on chip (they are used once per iteration, by one warp, on the critical path)
+                    const int blkD = bs * S.ow;
+                    for (int k = tid; k < bb; k += kST) sMid[k] = gDinv[(size_t)h * bb + k];
+                    for (int k = tid; k < blkD; k += kST) {
+                        sMid[bb + k] = h > 0 ? gOff[(size_t)(h - 1) * blkD + k] : 0.0;
+                        sMid[bb + blkD + k] = h < T - 1 ? gOff[(size_t)h * blkD + k] : 0.0;
+                    }
+                }
                 __syncthreads();
                 need_factor = false;
                 w_dirty = true;
@@ -629,7 +753,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                     ra -= gq[p];
                     rb -= gq[p2];
                 }
-                col_dot_ell2(S, X, np, p, p2, gA, gW, ra, rb);
+                col_dot2(p, p2, gW, ra, rb);
                 sRHS[p] = ra;
                 if (two) sRHS[p2] = rb;
             }
@@ -637,6 +761,64 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             SMARK(PH_RHS);
 
             // ---------------- block-tridiagonal solve in place on sRHS (warps 0 and 1)
+            const bool last = iter == st.max_iter;
+            const bool can_check = st.check_termination && (iter % st.check_termination == 0);
+            const bool adapt_now = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
+            const bool do_info = can_check || adapt_now || last;
+            const bool fastp = BS > 0 && BS <= 16 && upat && S.ow <= 2 && S.owT <= 2;
+            if (warp == 2 && fastp) {
+                // ---- producer warp of the fast path: keeps both chains' rings filled.  Lane c walks the groups of chain c
+                // (issuing a group's bulk copies costs several hundred cycles, so the two chains get a lane each); a slot
+                // is refilled as soon as its consumer has released it ("empty" barrier).
+                if (lane < 2) {
+                    const int blkD = bs * S.ow, grpD = X.grp * (bb + blkD);
+                    const int L0 = h, L1 = T - 1 - h;
+                    const int ng0 = 2 * ((L0 + X.grp - 1) / X.grp), ng1 = 2 * ((L1 + X.grp - 1) / X.grp);
+                    fence_proxy_async();
+                    // lane c serves chain c.  Groups [pre, ngc) of this solve (the first `pre` were issued at the end of the
+                    // previous one), then -- when another iteration is certain to follow with the same factor, i.e. no
+                    // residual check / rho update / iteration limit now -- the first groups of the next solve, so that its
+                    // sweeps do not start with an L2 round trip.
+                    {
+                        const int c = lane;
+                        const int ngc = c ? ng1 : ng0, L = c ? L1 : L0, ngh = ngc / 2;
+                        const uint32_t base = c ? prod_k1 : prod_k0;
+                        const int ahead = do_info ? 0 : min(X.grp_ring, ngc);
+                        for (int gq = pre; gq < ngc + ahead; ++gq) {
+                            const int gi = gq < ngc ? gq : gq - ngc; // group within its solve
+                            const bool first = gi < ngh;
+                            const int k = first ? gi : gi - ngh;
+                            const int cnt = min(X.grp, L - k * X.grp);
+                            int t0, dir, tbo;
+                            if (c == 0) {
+                                if (first) { t0 = k * X.grp; dir = 1; tbo = -1; }
+                                else { t0 = h - 1 - k * X.grp; dir = -1; tbo = 0; }
+                            } else {
+                                if (first) { t0 = T - 1 - k * X.grp; dir = -1; tbo = 0; }
+                                else { t0 = h + 1 + k * X.grp; dir = 1; tbo = -1; }
+                            }
+                            const uint32_t kk = base + (uint32_t)gq, slot = kk % X.grp_ring, round = kk / X.grp_ring;
+                            uint64_t *fullb = sFull + c * kStreamRing + slot, *emptyb = sEmpty + c * kStreamRing + slot;
+                            {
+                                unsigned spins = 0; // first use of a slot: the wait on the previous phase passes at once
+                                while (!mbar_try_wait(emptyb, (round & 1u) ^ 1u)) {
+                                    if (++spins > (1u << 26)) __trap();
+                                }
+                            }
+                            double *dst = sRing + (size_t)c * X.ring_doubles + (size_t)slot * grpD;
+                            const int tlo = dir > 0 ? t0 : t0 - cnt + 1;
+                            const int b_lo = max(tlo + tbo, 0), b_hi = min(tlo + cnt - 1 + tbo, T - 2);
+                            const uint32_t bytesD = (uint32_t)(cnt * bb) * 8u, bytesO = b_hi >= b_lo ? (uint32_t)((b_hi - b_lo + 1) * blkD) * 8u : 0u;
+                            mbar_expect_tx(fullb, bytesD + bytesO);
+                            bulk_g2s(dst, gDinv + (size_t)tlo * bb, bytesD, fullb);
+                            if (bytesO) bulk_g2s(dst + X.grp * bb + (b_lo - (tlo + tbo)) * blkD, gOff + (size_t)b_lo * blkD, bytesO, fullb);
+                        }
+                        pre = ahead;
+                    }
+                    prod_k0 += (uint32_t)ng0;
+                    prod_k1 += (uint32_t)ng1;
+                }
+            }
             if (warp < 2) {
                 const bool two_chains = T - 1 - h > 0; // T <= 2: the bottom chain is empty, warp 1 has nothing to wait for
                 double *ring = sRing + (size_t)warp * X.ring_doubles;
@@ -683,52 +865,37 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                         if (two_chains) named_bar_sync(1, 64);
                         Step sp;
                         sp.t = h; sp.ob = h - 1; sp.kind = 2;
-                        substep(sp, gDinv + (size_t)h * bb, gOff + (size_t)max(h - 1, 0) * bs * S.ow, gOff + (size_t)h * bs * S.ow, vb);
+                        substep(sp, sMid, sMid + bb, sMid + bb + bs * S.ow, vb);
                         if (two_chains) named_bar_sync(2, 64);
                     } else if (two_chains) {
                         named_bar_sync(1, 64);
                         named_bar_sync(2, 64);
                     }
                 };
-                const bool fast = BS > 0 && BS <= 16 && upat && S.ow <= 2 && S.owT <= 2;
+                const bool fast = fastp;
                 if (fast) {
-                    // ---- fast path: the factor streams in groups of kStreamGroup stages (one bulk copy for the
+                    // ---- fast path: the factor streams in groups of X.grp stages (one bulk copy for the
                     // pivot-block inverses, one for the off-diagonal blocks); inside a group the hand-scheduled
                     // sweep of the resident kernel runs on the slot as if it were the resident factor
                     const int L = warp == 0 ? h : T - 1 - h; // stages of this chain
-                    const int ng = (L + kStreamGroup - 1) / kStreamGroup, ngroups = 2 * ng;
-                    const int blkD = bs * S.ow, grpD = kStreamGroup * (bb + blkD);
+                    const int ng = (L + X.grp - 1) / X.grp, ngroups = 2 * ng;
+                    const int blkD = bs * S.ow, grpD = X.grp * (bb + blkD);
                     struct Grp { int t0, cnt, dir, tbo; bool fwd; };
                     auto group_of = [&](int gi) {
                         Grp g;
                         const bool first = gi < ng;
                         const int k = first ? gi : gi - ng;
-                        g.cnt = min(kStreamGroup, L - k * kStreamGroup);
+                        g.cnt = min(X.grp, L - k * X.grp);
                         g.fwd = first;
                         if (warp == 0) {
-                            if (first) { g.t0 = k * kStreamGroup; g.dir = 1; g.tbo = -1; }
-                            else { g.t0 = h - 1 - k * kStreamGroup; g.dir = -1; g.tbo = 0; }
+                            if (first) { g.t0 = k * X.grp; g.dir = 1; g.tbo = -1; }
+                            else { g.t0 = h - 1 - k * X.grp; g.dir = -1; g.tbo = 0; }
                         } else {
-                            if (first) { g.t0 = T - 1 - k * kStreamGroup; g.dir = -1; g.tbo = 0; }
-                            else { g.t0 = h + 1 + k * kStreamGroup; g.dir = 1; g.tbo = -1; }
+                            if (first) { g.t0 = T - 1 - k * X.grp; g.dir = -1; g.tbo = 0; }
+                            else { g.t0 = h + 1 + k * X.grp; g.dir = 1; g.tbo = -1; }
                         }
                         return g;
                     };
-                    auto issue_group = [&](int gi) { // lane 0
-                        const Grp g = group_of(gi);
-                        const int tlo = g.dir > 0 ? g.t0 : g.t0 - g.cnt + 1;
-                        const uint32_t slot = (ring_k + (uint32_t)gi) % kStreamGroupRing;
-                        double *dst = ring + (size_t)slot * grpD;
-                        const int b_lo = max(tlo + g.tbo, 0), b_hi = min(tlo + g.cnt - 1 + g.tbo, T - 2);
-                        const uint32_t bytesD = (uint32_t)(g.cnt * bb) * 8u, bytesO = b_hi >= b_lo ? (uint32_t)((b_hi - b_lo + 1) * blkD) * 8u : 0u;
-                        mbar_expect_tx(full + slot, bytesD + bytesO);
-                        bulk_g2s(dst, gDinv + (size_t)tlo * bb, bytesD, full + slot);
-                        if (bytesO) bulk_g2s(dst + kStreamGroup * bb + (b_lo - (tlo + g.tbo)) * blkD, gOff + (size_t)b_lo * blkD, bytesO, full + slot);
-                    };
-                    if (lane == 0) {
-                        fence_proxy_async();
-                        for (int gi = 0; gi < kStreamGroupRing - 1 && gi < ngroups; ++gi) issue_group(gi);
-                    }
                     const uint32_t rhs0 = smem_u32(sRHS), vb0 = smem_u32(vb), ring0 = smem_u32(ring);
                     const uint32_t blk_bytes = (uint32_t)blkD * 8u;
                     // per-lane pattern constants: forward = row r of the block above, transposed = column r of the block below
@@ -746,18 +913,18 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                             middle();
                             prev = sRHS[h * bs + r];
                         }
-                        // the slot consumed one group ago is free (its reads retired inside the sweep): refill it
-                        if (lane == 0 && gi + kStreamGroupRing - 1 < ngroups) issue_group(gi + kStreamGroupRing - 1);
                         const Grp g = group_of(gi);
-                        const uint32_t kk = ring_k + (uint32_t)gi, slot = kk % kStreamGroupRing;
-                        wait_slot(slot, (kk / kStreamGroupRing) & 1u);
+                        const uint32_t kk = ring_k + (uint32_t)gi, slot = kk % X.grp_ring;
+                        wait_slot(slot, (kk / X.grp_ring) & 1u);
                         const int tlo = g.dir > 0 ? g.t0 : g.t0 - g.cnt + 1;
                         const uint32_t sl = ring0 + slot * (uint32_t)grpD * 8u;
                         const uint32_t dinv0 = sl - (uint32_t)(tlo * bb) * 8u;                                    // virtual base: stage t at + t*bb*8
-                        const uint32_t off0 = sl + (uint32_t)(kStreamGroup * bb) * 8u - (uint32_t)(tlo + g.tbo) * blk_bytes; // block tb at + tb*blk_bytes
+                        const uint32_t off0 = sl + (uint32_t)(X.grp * bb) * 8u - (uint32_t)(tlo + g.tbo) * blk_bytes; // block tb at + tb*blk_bytes
                         const bool tr = g.tbo == 0;
                         prev = chain_sweep_ool<BS>(dinv0, rhs0, off0, vb0, g.t0, g.cnt, g.dir, g.tbo, T - 1, blk_bytes, g.fwd, prev, lane,
                                                tr ? tg0 : fg0, tr ? tg1 : fg1, tr ? to0 : fo0, tr ? to1 : fo1, tr ? th0 : fh0, tr ? th1 : fh1);
+                        __syncwarp(); // every lane's reads of the slot have retired: hand it back to the producer warp
+                        if (lane == 0) mbar_arrive(sEmpty + warp * kStreamRing + slot);
                     }
                     ring_k += (uint32_t)ngroups;
                 } else {
@@ -765,7 +932,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                     const int nsteps = warp == 0 ? 2 * h + 1 : 2 * (T - 1 - h);
                     auto issue = [&](int j) { // lane 0: start the bulk copies of step j
                         const Step sp = step_of(warp, j, T, h);
-                        const uint32_t slot = (ring_k + (uint32_t)j) % kStreamRing;
+                        const uint32_t slot = (ring_k + (uint32_t)j) % (uint32_t)X.gen_ring;
                         double *dst = ring + (size_t)slot * slotD;
                         const uint32_t bytesD = (uint32_t)bb * 8u, bytesO = (uint32_t)(bs * S.ow) * 8u;
                         const bool has_off = sp.ob >= 0 && sp.ob < T - 1;
@@ -775,7 +942,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                     };
                     if (lane == 0) {
                         fence_proxy_async();
-                        for (int j = 0; j < kStreamRing - 1 && j < nsteps; ++j) issue(j);
+                        for (int j = 0; j < X.gen_ring - 1 && j < nsteps; ++j) issue(j);
                     }
 #pragma unroll 1
                     for (int j = 0; j < nsteps; ++j) {
@@ -787,9 +954,9 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                         }
                         // the slot consumed one step ago is free: refill it kStreamRing-1 steps ahead
                         // (its last generic-proxy reads retired before the previous step's closing __syncwarp)
-                        if (lane == 0 && j + kStreamRing - 1 < nsteps) issue(j + kStreamRing - 1);
-                        const uint32_t kk = ring_k + (uint32_t)j, slot = kk % kStreamRing;
-                        wait_slot(slot, (kk / kStreamRing) & 1u);
+                        if (lane == 0 && j + X.gen_ring - 1 < nsteps) issue(j + X.gen_ring - 1);
+                        const uint32_t kk = ring_k + (uint32_t)j, slot = kk % (uint32_t)X.gen_ring;
+                        wait_slot(slot, (kk / (uint32_t)X.gen_ring) & 1u);
                         const double *Dm = ring + (size_t)slot * slotD, *Ob = Dm + bb;
                         // kinds 0, 2, 4 stream Off_{t-1}; kinds 1, 3 stream Off_t; the middle stage reads Off_h from L2
                         substep(sp, Dm, Ob, sp.kind == 2 ? gOff + (size_t)sp.t * bs * S.ow : Ob, vb + (j & 1) * 32);
@@ -802,10 +969,6 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             __syncthreads();
             SMARK(PH_SOLVE);
 
-            const bool last = iter == st.max_iter;
-            const bool can_check = st.check_termination && (iter % st.check_termination == 0);
-            const bool adapt_now = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
-            const bool do_info = can_check || adapt_now || last;
             // ---------------- x, z, y updates
             for (int p = tid; p < np; p += kST) {
                 const double xo = gx[p];
@@ -815,7 +978,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             }
             ROWS2(i, i2, two) {
                 double zta, ztb;
-                row_dot_ell2(X, mu, i, i2, gA, sRHS, zta, ztb);
+                row_dot2(i, i2, sRHS, zta, ztb);
                 const double rva = gRho[i], zoa = gz[i], yoa = gy[i], loa = gLo[i], hia = gHi[i];
                 const double rvb = gRho[i2], zob = gz[i2], yob = gy[i2], lob = gLo[i2], hib = gHi[i2];
                 {
@@ -848,7 +1011,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                     double na[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
                     ROWS2(i, i2, two) {
                         double axa, axb;
-                        row_dot_ell2(X, mu, i, i2, gA, gx, axa, axb);
+                        row_dot2(i, i2, gx, axa, axb);
 #pragma unroll
                         for (int w = 0; w < 2; ++w) {
                             if (w == 1 && !two) break;
@@ -872,7 +1035,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                     double nb[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
                     COLS2(p0, p2, two) {
                       double atya = 0.0, atyb = 0.0;
-                      col_dot_ell2(S, X, np, p0, p2, gA, gy, atya, atyb);
+                      col_dot2(p0, p2, gy, atya, atyb);
 #pragma unroll
                       for (int w = 0; w < 2; ++w) {
                         if (w == 1 && !two) break;
@@ -951,7 +1114,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                         if (nrm[0] > kDivTol && lhs < -epi * nrm[0]) {
                             double v[1] = {0.0};
                             for (int p = tid; p < np; p += kST) {
-                                const double acc = col_dot_g(S, p, gA, gW, 0.0);
+                                const double acc = col_dot1(p, gW);
                                 v[0] = fmax(v[0], fabs(uns ? (1.0 / gD[p]) * acc : acc));
                             }
                             block_max<1, NT>(v, sRed, tid);
@@ -983,7 +1146,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                             if (v[0] < cs_ * edi * nrm[0]) {
                                 double viol[1] = {0.0};
                                 for (int i = tid; i < mu; i += kST) {
-                                    double acc = row_dot_g(S, i, gA, gdx);
+                                    double acc = row_dot1(i, gdx);
                                     if (uns) acc *= 1.0 / gE[i];
                                     if ((gHi[i] < kInfty * kMinScaling && acc > edi * nrm[0]) ||
                                         (gLo[i] > -kInfty * kMinScaling && acc < -edi * nrm[0]))
@@ -1041,34 +1204,29 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
     }
 }
 
-static int stream_threads() {
-    const char *e = std::getenv("GOMP_STREAM_THREADS");
-    return (e && std::atoi(e) == 256) ? 256 : 512;
-}
-cudaError_t prepare_stream(int bs, size_t smem_bytes, int *ctas_per_sm) {
-    const int nt = stream_threads();
+cudaError_t prepare_stream(int bs, bool small, size_t smem_bytes, int *ctas_per_sm) {
     cudaError_t e;
-#define PREP(FN)                                                                                          \
+#define PREP(FN, NTHR)                                                                                    \
     e = cudaFuncSetAttribute(FN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);           \
     if (e != cudaSuccess) return e;                                                                       \
     cudaFuncSetAttribute(FN, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, FN, nt, smem_bytes);
-    if (nt == 256) {
-        if (bs == 14) { PREP((gomp_admm_stream_kernel<14, 256>)) }
-        PREP((gomp_admm_stream_kernel<0, 256>))
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, FN, NTHR, smem_bytes);
+    if (small) {
+        if (bs == 14) { PREP((gomp_admm_stream_kernel<14, kStreamSmallThreads, true>), kStreamSmallThreads) }
+        PREP((gomp_admm_stream_kernel<0, kStreamSmallThreads, true>), kStreamSmallThreads)
     }
-    if (bs == 14) { PREP((gomp_admm_stream_kernel<14, 512>)) }
-    PREP((gomp_admm_stream_kernel<0, 512>))
+    if (bs == 14) { PREP((gomp_admm_stream_kernel<14, kStreamThreads, false>), kStreamThreads) }
+    PREP((gomp_admm_stream_kernel<0, kStreamThreads, false>), kStreamThreads)
 #undef PREP
 }
 cudaError_t launch_stream(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int grid, size_t smem_bytes,
                           cudaStream_t stream) {
-    if (stream_threads() == 256) {
-        if (S.bs == 14) gomp_admm_stream_kernel<14, 256><<<grid, 256, smem_bytes, stream>>>(S, B, st, X);
-        else gomp_admm_stream_kernel<0, 256><<<grid, 256, smem_bytes, stream>>>(S, B, st, X);
+    if (X.small) {
+        if (S.bs == 14) gomp_admm_stream_kernel<14, kStreamSmallThreads, true><<<grid, kStreamSmallThreads, smem_bytes, stream>>>(S, B, st, X);
+        else gomp_admm_stream_kernel<0, kStreamSmallThreads, true><<<grid, kStreamSmallThreads, smem_bytes, stream>>>(S, B, st, X);
     } else {
-        if (S.bs == 14) gomp_admm_stream_kernel<14, 512><<<grid, 512, smem_bytes, stream>>>(S, B, st, X);
-        else gomp_admm_stream_kernel<0, 512><<<grid, 512, smem_bytes, stream>>>(S, B, st, X);
+        if (S.bs == 14) gomp_admm_stream_kernel<14, kStreamThreads, false><<<grid, kStreamThreads, smem_bytes, stream>>>(S, B, st, X);
+        else gomp_admm_stream_kernel<0, kStreamThreads, false><<<grid, kStreamThreads, smem_bytes, stream>>>(S, B, st, X);
     }
     return cudaGetLastError();
 }

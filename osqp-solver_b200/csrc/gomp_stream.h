@@ -8,8 +8,10 @@
 namespace gomp_dev {
 
 constexpr int kStreamRing = 8;      // generic path: factor slots (one stage each) in flight per substitution warp
-constexpr int kStreamGroup = 8;     // fast path: stages per bulk copy
-constexpr int kStreamGroupRing = 3; // fast path: groups in flight per substitution warp
+constexpr int kStreamGroup = 8;     // fast path: stages per bulk copy (long horizons)
+constexpr int kStreamGroupRing = 3; // fast path: groups in flight per substitution warp (long horizons)
+constexpr int kStreamSmallThreads = 256; // small-QP mode: threads per CTA (two CTAs per SM)
+constexpr int kStreamSmallGroup = 4, kStreamSmallGroupRing = 2; // ... and its ring geometry
 constexpr int kStreamThreads = 512; // threads per CTA of the streamed kernel
 
 struct DevStream {
@@ -19,15 +21,19 @@ struct DevStream {
     // rho per row, pivot-block inverses [T][bs][bs], ELL off-diagonal blocks, column scratch, scaled bounds
     long long wA, wP, wW, wRho, wDinv, wOff, wT, wLo, wHi;
     // shared memory (byte offsets)
-    int oRHS, oRing, oPub, oDprev, oOffBuf, oV, oRed, oBar;
+    int oRHS, oRing, oPub, oDprev, oOffBuf, oV, oMid, oRed, oBar;
     const uint32_t *row_ell; // [roww][m_used] (pos << 16 | value index), 0xFFFFFFFF = none
     const uint16_t *col_ell; // [colw][n_pad] compact row of the j-th entry of a column
     int roww, colw;
+    int gen_ring;      // generic path: ring slots (one stage each) per substitution warp, <= kStreamRing
+    int grp, grp_ring; // fast path: stages per bulk copy, groups in flight per substitution warp
+    int small;         // small-QP mode: A values, w and the CSR / CSC pattern arrays in shared memory, 256 threads per CTA
+    int oA, oW, oRowEnt, oRowRange, oColRange, oCscRow; // ... their byte offsets
     int slot_doubles; // bs*bs + bs*ow, one ring slot
     int ring_doubles; // ring size per substitution warp
 };
 
-cudaError_t prepare_stream(int bs, size_t smem_bytes, int *ctas_per_sm);
+cudaError_t prepare_stream(int bs, bool small, size_t smem_bytes, int *ctas_per_sm);
 cudaError_t launch_stream(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int grid, size_t smem_bytes,
                           cudaStream_t stream);
 

@@ -26,5 +26,6 @@ for linsys in (1, 2):
         its = out['iters'].sum() * 2
         names = ['load', 'scale', 'factor', 'rhs', 'solve', 'update', 'info', 'store']
         print('   per iteration: ' + ', '.join(f'{n} {ph[k] / its:.0f}' for k, n in enumerate(names) if n in ('rhs', 'solve', 'update')),
-              '| per QP: ' + ', '.join(f'{n} {ph[k] / (batch * 2):.0f}' for k, n in enumerate(names) if n not in ('rhs', 'solve', 'update')))
+              '| per QP: ' + ', '.join(f'{n} {ph[k] / (batch * 2):.0f}' for k, n in enumerate(names) if n not in ('rhs', 'solve', 'update')),
+              '| chain (warp 0) per iteration %.0f' % (info['chain_cycles'] / its))
     s.close()
