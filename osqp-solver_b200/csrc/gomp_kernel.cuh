@@ -435,100 +435,6 @@ __device__ __forceinline__ double chain_sweep_impl(uint32_t dinv0, uint32_t rhs0
     }
     return prev;
 }
-// The same sweep over a factor that STREAMS through a ring of shared-memory slots (streamed back end): the stages come in
-// groups of `grp` -- slot layout [grp pivot-block inverses | grp off-diagonal blocks], filled by a producer warp with
-// bulk copies -- and the loop itself waits for a group's "full" barrier when it enters the group and hands the slot
-// back ("empty" barrier) when it leaves it, so a whole sweep is one call however many groups it spans.
-//   ring0 / slot_bytes: first slot and slot pitch; full0 / empty0: shared-window addresses of the two barrier arrays
-//   (8 bytes per slot); kk0: groups this chain has consumed before this sweep (slot = kk % ring, parity from kk / ring).
-template <int BS, bool fwd>
-static __device__ __noinline__ double chain_sweep_ring(uint32_t ring0, uint32_t slot_bytes, int grp, int ring, uint32_t full0, uint32_t empty0,
-                                                       uint32_t kk0, uint32_t rhs0, uint32_t vb0, int t0, int count, int dir, int tbo,
-                                                       int nblk, uint32_t blk_bytes, double prev, int lane, int g0, int g1, uint32_t o0,
-                                                       uint32_t o1, bool has0, bool has1) {
-    constexpr int NB = BS > 0 ? BS : 2;
-    constexpr int CH = ((NB / 2) + 1) & ~1;
-    constexpr int NC = CH > NB - CH ? CH : NB - CH;
-    const int r = lane & 15, half = lane >> 4;
-    const int rl = r < NB ? r : NB - 1;
-    const bool act = half == 0 && r < NB;
-    const int c0 = half ? CH : 0, nc = half ? NB - CH : CH;
-    uint32_t ab = rhs0 + (uint32_t)(t0 * NB + rl) * 8u;
-    int t = t0, tb = t0 + tbo;
-    uint32_t par = (uint32_t)(t0 & 1) * 128u;
-    const uint32_t darow = (uint32_t)(dir * NB * NB * 8), dab = (uint32_t)(dir * NB * 8), dao = (uint32_t)dir * blk_bytes;
-    uint32_t arow = 0, ao = 0, kk = kk0, slot = 0;
-    int left = 0; // stages left in the current group
-#pragma unroll 1
-    for (int it = 0; it < count; ++it) {
-        if (left == 0) { // enter the next group: wait for its slot, derive the running addresses inside it
-            left = min(grp, count - it);
-            slot = kk % (uint32_t)ring;
-            const uint32_t parity = (kk / (uint32_t)ring) & 1u;
-            unsigned spins = 0;
-            for (;;) {
-                uint32_t ok;
-                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                             : "=r"(ok)
-                             : "r"(full0 + slot * 8u), "r"(parity)
-                             : "memory");
-                if (ok) break;
-                if (++spins > (1u << 26)) __trap();
-            }
-            const int tlo = dir > 0 ? t : t - left + 1; // the slot holds stages tlo .. tlo + left - 1 in ascending order
-            const uint32_t sl = ring0 + slot * slot_bytes;
-            arow = sl + (uint32_t)(((t - tlo) * NB + rl) * NB + c0) * 8u;
-            ao = sl + (uint32_t)(grp * NB * NB) * 8u + (uint32_t)(tb - (tlo + tbo)) * blk_bytes;
-        }
-        double m[NC];
-#pragma unroll
-        for (int c = 0; c < NC; c += 2) {
-            if (c < nc) {
-                const double2 d = lds_f64x2(arow + (uint32_t)c * 8u);
-                m[c] = d.x;
-                m[c + 1] = d.y;
-            } else {
-                m[c] = 0.0;
-                m[c + 1] = 0.0;
-            }
-        }
-        const double b = lds_f64(ab);
-        const bool blk = (unsigned)tb < (unsigned)nblk;
-        const double ov0 = (blk && has0) ? lds_f64(ao + o0) : 0.0;
-        const double ov1 = (blk && has1) ? lds_f64(ao + o1) : 0.0;
-        const double up0 = __shfl_sync(0xffffffffu, prev, g0);
-        const double up1 = __shfl_sync(0xffffffffu, prev, g1);
-        const double off = fma(ov0, up0, ov1 * up1);
-        const double v = fwd ? b - off : off;
-        const uint32_t avb = vb0 + par;
-        if (act) sts_f64(avb + (uint32_t)r * 8u, v);
-        __syncwarp();
-        double2 w[NC / 2];
-#pragma unroll
-        for (int c = 0; c < NC; c += 2) w[c / 2] = c < nc ? lds_f64x2(avb + (uint32_t)(c0 + c) * 8u) : make_double2(0.0, 0.0);
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-        for (int c = 0; c < NC; c += 2) {
-            a0 = fma(m[c], w[c / 2].x, a0);
-            a1 = fma(m[c + 1], w[c / 2].y, a1);
-        }
-        double acc = a0 + a1;
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        prev = fwd ? acc : b - acc;
-        if (act) sts_f64(ab, prev);
-        arow += darow;
-        ab += dab;
-        ao += dao;
-        tb += dir;
-        t += dir;
-        par ^= 128u;
-        if (--left == 0) { // leave the group: every lane's loads of the slot were consumed before the shuffle above
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + slot * 8u) : "memory");
-            ++kk;
-        }
-    }
-    return prev;
-}
 // Out-of-line instances (one per sweep direction of the recurrence): scheduled and register-allocated on their own,
 // whatever surrounds the call -- the inlined copies lost 20-30 % to the code around them.
 template <int BS, bool fwd>
