@@ -131,3 +131,13 @@ def test_random_block_tridiagonal_qps(bs, T):
         if r.exit_code == 0:
             assert np.abs(got["x"][b] - r.x).max() < 1e-6 * max(1.0, np.abs(r.x).max())
             assert np.abs(got["y"][b] - r.y).max() < 1e-6 * max(1.0, np.abs(r.y).max())
+
+
+def test_long_horizon_shape_on_the_emulator():
+    """BASELINE configs[3] shape (N = 7, H = 400) through the product's symbolic analysis and the sequential
+    walk-through of the device algorithm: same status, iterations and solution as the oracle (no GPU needed)."""
+    pkg, O = package(), oracle()
+    pat, d, E, got, ref = run_pair(pkg, O, dict(waypoints=400), 2, first=40)
+    assert (pat.n, pat.m, pat.nnzA) == (5600, 22372, 30730)
+    assert (E.bs, E.T, E.n_pad, E.ow, E.owT) == (14, 400, 5600, 2, 2)
+    check(got, ref)
