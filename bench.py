@@ -170,7 +170,9 @@ def run_gpu(args):
 
     def make(borrow, stream):
         st = S.default_settings(borrow_inputs=1 if borrow else 0, stream=stream.cuda_stream, device=local_rank,
-                                linsys=int(os.environ.get("GOMP_BENCH_LINSYS", "0")))  # 0 = AUTO (the measured configuration)
+                                linsys=int(os.environ.get("GOMP_BENCH_LINSYS", "0")),  # 0 = AUTO (the measured configuration)
+                                # several independent batches are kept in flight: let AUTO take the two-QPs-per-SM mode
+                                prefer_throughput=int(os.environ.get("GOMP_BENCH_THROUGHPUT", "1")))
         return S.BatchQPSolver(pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx,
                                batch=B, settings=st, var_order=pat.var_order, block_size=pat.block_size)
 
@@ -315,7 +317,8 @@ def run_gpu(args):
     ksec = kernel_avg_ms * 1e-3
     # DRAM bytes of one launch from the committed ncu --set full capture (same kernel, same workload)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    streamed = int(info["linsys"]) == 2  # AUTO + prefer_throughput: the two-QPs-per-SM mode of the streamed kernel
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic_stream.json" if streamed else "r01_ncu_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * B / tj["qps_per_launch"]
@@ -324,7 +327,7 @@ def run_gpu(args):
                 "frac": smem_bytes / ksec / 1e9 / smem_peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_hbm_bytes": hbm_bytes,
                 "peak_source": "measured live (gomp_measure_peaks: conflict-free 16-byte shared-memory loads on all SMs)",
-                "kernel": "gomp_admm_kernel", "kernel_ms": kernel_avg_ms,
+                "kernel": "gomp_admm_stream_kernel<14,256,true>" if streamed else "gomp_admm_kernel<4,2,14>", "kernel_ms": kernel_avg_ms,
                 "fp64": {"achieved": flops / ksec / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops / ksec / 1e12 / fp64_peak,
                          "peak_source": "measured live (gomp_measure_peaks: 8 independent DFMA chains per thread)"},
                 "hbm": {"achieved": hbm_bytes / ksec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_bytes / ksec / 1e9 / hbm_peak,

@@ -420,6 +420,7 @@ int gomp_settings_default(gomp_settings *s) {
     s->var_order = nullptr;
     s->threads_per_cta = 0;
     s->borrow_inputs = 0;
+    s->prefer_throughput = 0;
     return GOMP_OK;
 }
 
@@ -554,9 +555,61 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     cudaEventCreate(&h->evc1);
     if ((rc = upload_pattern(h))) return bail(rc);
 
+    // ---- streamed back end: shared-memory layout (needed before the back end is chosen: prefer_throughput)
+    const gomp::Symbolic &s = h->sym;
+    DevStream &x = h->dx;
+    size_t o = 0;
+    auto take = [&o](size_t bytes) {
+        size_t at = o;
+        o += (bytes + 15) & ~(size_t)15;
+        return (int)at;
+    };
+    x.slot_doubles = s.bs * s.bs + s.bs * s.ow;
+    // the grouped ring (fast path of gomp_stream.cu: compile-time block size 14, uniform 2-wide off-diagonal pattern)
+    // needs grp * grp_ring stage slots per warp, the generic path kStreamRing
+    const bool grouped = s.bs == 14 && h->ds.uniform_off && s.ow <= 2 && s.owT <= 2;
+    auto layout = [&](bool small) {
+        o = 0;
+        x.small = small ? 1 : 0;
+        x.grp = small ? kStreamSmallGroup : kStreamGroup;
+        x.grp_ring = small ? kStreamSmallGroupRing : kStreamGroupRing;
+        x.oRHS = take(8 * (size_t)s.n_pad);
+        // generic path: as many one-stage slots as fit beside the fixed regions (at least 3, at most kStreamRing)
+        x.gen_ring = kStreamRing;
+        if (!grouped) {
+            const size_t fixed = 8 * (size_t)s.n_pad + 8 * ((size_t)3 * s.bs * s.bs + (size_t)4 * s.bs * std::max(1, s.ow)) + 8192;
+            const size_t room = (size_t)prop.sharedMemPerBlockOptin > fixed ? (size_t)prop.sharedMemPerBlockOptin - fixed : 0;
+            x.gen_ring = (int)std::max<size_t>(3, std::min<size_t>(kStreamRing, room / (2 * 8 * (size_t)x.slot_doubles)));
+        }
+        x.ring_doubles = (grouped ? std::max(small ? 0 : kStreamRing, x.grp * x.grp_ring) : x.gen_ring) * x.slot_doubles;
+        x.oRing = take(8 * (size_t)2 * x.ring_doubles);
+        const int groups = 2; // factor groups: 2 x 224 threads, or 2 x 112 in the 256-thread CTAs of the small-QP mode
+        x.oPub = take(8 * (size_t)128 * groups);
+        x.oDprev = take(8 * (size_t)groups * s.bs * s.bs);
+        x.oOffBuf = take(8 * (size_t)groups * s.bs * std::max(1, s.ow));
+        x.oV = take(8 * 128);
+        x.oMid = take(8 * ((size_t)s.bs * s.bs + 2 * (size_t)s.bs * std::max(1, s.ow)));
+        x.oRed = take(8 * (size_t)kRedK * ((small ? kStreamSmallThreads : kStreamThreads) / 32));
+        x.oBar = take(8 * 4 * kStreamRing + 16); // full + empty barriers of both chains, work-queue slot
+        x.oA = x.oW = x.oRowEnt = x.oRowRange = x.oColRange = x.oCscRow = 0;
+        if (small) {
+            x.oA = take(8 * (size_t)s.nnzA);
+            x.oW = take(8 * (size_t)std::max(1, s.m_used));
+            x.oRowEnt = take(4 * ((size_t)s.nnzA + 4));
+            x.oRowRange = take(2 * ((size_t)s.m_used + 2)); // 16-bit CSR row pointers
+            x.oColRange = take(4 * (size_t)s.n_pad);
+            x.oCscRow = take(2 * ((size_t)s.nnzA + 4));
+        }
+        return o;
+    };
+    // small-QP mode: two 256-thread CTAs per SM, sparse data in shared memory -- when a CTA fits half an SM
+    const size_t half_sm = (size_t)prop.sharedMemPerMultiprocessor / 2 - 1024;
+    const bool small_ok = s.bs % 2 == 0 && s.bs <= 32 && grouped && !std::getenv("GOMP_STREAM_NO_SMALL") && layout(true) <= half_sm;
+
     h->kernel = pick_kernel(h->sym.m_used, h->sym.n_pad, h->sym.bs);
     const bool resident_ok = h->kernel.launch && h->smem_bytes <= (size_t)prop.sharedMemPerBlockOptin;
-    h->streamed = st.linsys == GOMP_LINSYS_BLOCKTRI_GLOBAL || (st.linsys == GOMP_LINSYS_AUTO && !resident_ok);
+    h->streamed = st.linsys == GOMP_LINSYS_BLOCKTRI_GLOBAL ||
+                  (st.linsys == GOMP_LINSYS_AUTO && (!resident_ok || (st.prefer_throughput && small_ok && batch >= 2 * (int64_t)h->num_sms)));
     int occ = 0;
     if (!h->streamed) {
         if (!h->kernel.launch)
@@ -568,57 +621,9 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
         if (occ < 1) return bail(fail(GOMP_ERR_CUDA, "kernel cannot be resident (occupancy 0)"));
     } else {
         // long-horizon back end: x~ in shared memory, everything else in a per-CTA global workspace
-        const gomp::Symbolic &s = h->sym;
-        DevStream &x = h->dx;
         if (s.bs % 2 != 0 || s.bs > 32)
             return bail(fail(GOMP_ERR_UNSUPPORTED, "streamed back end needs an even block size <= 32 (16-byte bulk copies)"));
-        size_t o = 0;
-        auto take = [&o](size_t bytes) {
-            size_t at = o;
-            o += (bytes + 15) & ~(size_t)15;
-            return (int)at;
-        };
-        x.slot_doubles = s.bs * s.bs + s.bs * s.ow;
-        // the grouped ring (fast path of gomp_stream.cu: compile-time block size 14, uniform 2-wide off-diagonal pattern)
-        // needs grp * grp_ring stage slots per warp, the generic path kStreamRing
-        const bool grouped = s.bs == 14 && h->ds.uniform_off && s.ow <= 2 && s.owT <= 2;
-        auto layout = [&](bool small) {
-            o = 0;
-            x.small = small ? 1 : 0;
-            x.grp = small ? kStreamSmallGroup : kStreamGroup;
-            x.grp_ring = small ? kStreamSmallGroupRing : kStreamGroupRing;
-            x.oRHS = take(8 * (size_t)s.n_pad);
-            // generic path: as many one-stage slots as fit beside the fixed regions (at least 3, at most kStreamRing)
-            x.gen_ring = kStreamRing;
-            if (!grouped) {
-                const size_t fixed = 8 * (size_t)s.n_pad + 8 * ((size_t)3 * s.bs * s.bs + (size_t)4 * s.bs * std::max(1, s.ow)) + 8192;
-                const size_t room = (size_t)prop.sharedMemPerBlockOptin > fixed ? (size_t)prop.sharedMemPerBlockOptin - fixed : 0;
-                x.gen_ring = (int)std::max<size_t>(3, std::min<size_t>(kStreamRing, room / (2 * 8 * (size_t)x.slot_doubles)));
-            }
-            x.ring_doubles = (grouped ? std::max(small ? 0 : kStreamRing, x.grp * x.grp_ring) : x.gen_ring) * x.slot_doubles;
-            x.oRing = take(8 * (size_t)2 * x.ring_doubles);
-            const int groups = 2; // factor groups: 2 x 224 threads, or 2 x 112 in the 256-thread CTAs of the small-QP mode
-            x.oPub = take(8 * (size_t)128 * groups);
-            x.oDprev = take(8 * (size_t)groups * s.bs * s.bs);
-            x.oOffBuf = take(8 * (size_t)groups * s.bs * std::max(1, s.ow));
-            x.oV = take(8 * 128);
-            x.oMid = take(8 * ((size_t)s.bs * s.bs + 2 * (size_t)s.bs * std::max(1, s.ow)));
-            x.oRed = take(8 * (size_t)kRedK * ((small ? kStreamSmallThreads : kStreamThreads) / 32));
-            x.oBar = take(8 * 4 * kStreamRing + 16); // full + empty barriers of both chains, work-queue slot
-            x.oA = x.oW = x.oRowEnt = x.oRowRange = x.oColRange = x.oCscRow = 0;
-            if (small) {
-                x.oA = take(8 * (size_t)s.nnzA);
-                x.oW = take(8 * (size_t)std::max(1, s.m_used));
-                x.oRowEnt = take(4 * ((size_t)s.nnzA + 4));
-                x.oRowRange = take(2 * ((size_t)s.m_used + 2)); // 16-bit CSR row pointers
-                x.oColRange = take(4 * (size_t)s.n_pad);
-                x.oCscRow = take(2 * ((size_t)s.nnzA + 4));
-            }
-            return o;
-        };
-        // small-QP mode: two 256-thread CTAs per SM, sparse data in shared memory -- when a CTA fits half an SM
-        const size_t half_sm = (size_t)prop.sharedMemPerMultiprocessor / 2 - 1024;
-        bool small = grouped && !std::getenv("GOMP_STREAM_NO_SMALL") && layout(true) <= half_sm;
+        const bool small = small_ok;
         h->smem_bytes = layout(small);
         if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
             return bail(fail(GOMP_ERR_UNSUPPORTED, "right-hand side of the block solve does not fit in shared memory (" +

@@ -32,6 +32,7 @@ class Settings(C.Structure):
         ("scaled_termination", C.c_int32), ("check_termination", C.c_int32), ("warm_start", C.c_int32),
         ("verbose", C.c_int32), ("device", C.c_int32), ("stream", C.c_void_p), ("linsys", C.c_int32),
         ("block_size", C.c_int32), ("var_order", C.c_void_p), ("threads_per_cta", C.c_int32), ("borrow_inputs", C.c_int32),
+        ("prefer_throughput", C.c_int32),
     ]
 
 

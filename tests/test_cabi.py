@@ -43,6 +43,7 @@ def test_settings_defaults_match_osqp():
     assert (s.rho, s.sigma, s.alpha, s.scaling, s.adaptive_rho, s.max_iter) == (0.1, 1e-6, 1.6, 10, 1, 4000)
     assert (s.eps_abs, s.eps_rel, s.eps_prim_inf, s.eps_dual_inf) == (1e-3, 1e-3, 1e-4, 1e-4)
     assert (s.check_termination, s.adaptive_rho_interval, s.adaptive_rho_tolerance, s.warm_start) == (25, 25, 5.0, 1)
+    assert (s.linsys, s.borrow_inputs, s.prefer_throughput) == (0, 0, 0)
 
 
 def test_no_cpu_fallback_without_device():

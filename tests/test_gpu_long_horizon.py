@@ -166,3 +166,28 @@ def test_streamed_general_qp_with_linear_term():
         assert got["exit_code"][b] == r.exit_code and got["iters"][b] == r.iter
         assert np.abs(got["x"][b] - r.x).max() < REL_TOL * max(1.0, np.abs(r.x).max())
         assert np.abs(got["y"][b] - r.y).max() < REL_TOL * max(1.0, np.abs(r.y).max())
+
+
+def test_prefer_throughput_selects_two_ctas_per_sm():
+    """AUTO + prefer_throughput on the headline shape with a batch of >= 2 QPs per SM: the streamed kernel's
+    small-QP mode (256 threads, two CTAs per SM); same answers as the resident kernel.  Small batches stay resident."""
+    pkg, O = package(), oracle()
+    pat = pkg.problem.Pattern(pkg.problem.default_config())
+    B = 640
+    d = pkg.problem.generate(pat, 2000, B)
+    fast = make_solver(pkg, pat, d, settings=pkg.solver.default_settings(prefer_throughput=1))
+    info = fast.info()
+    assert info["linsys"] == GLOBAL and info["threads_per_cta"] == 256 and info["ctas_per_sm"] == 2
+    fast.set_warm_start(d["x0"])
+    got = fast.solve(want_y=True)
+    fast.close()
+    res = make_solver(pkg, pat, d)
+    assert res.info()["linsys"] == 1
+    res.set_warm_start(d["x0"])
+    ref = res.solve(want_y=True)
+    res.close()
+    compare(got, ref)
+    few = {k: v[:16] for k, v in d.items()}
+    s = make_solver(pkg, pat, few, settings=pkg.solver.default_settings(prefer_throughput=1))
+    assert s.info()["linsys"] == 1          # a handful of QPs: latency matters, resident kernel
+    s.close()

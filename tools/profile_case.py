@@ -14,8 +14,10 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 repeats = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 pat = P.Pattern(P.default_config())
 d = P.generate(pat, 0, batch)
+# GOMP_PROFILE_THROUGHPUT=1: the two-QPs-per-SM mode of the streamed back end (what bench.py measures), else the resident kernel
+st = S.default_settings(prefer_throughput=int(os.environ.get("GOMP_PROFILE_THROUGHPUT", "0")))
 s = S.BatchQPSolver(pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx, d["A_val"], d["l"], d["u"],
-                    var_order=pat.var_order, block_size=pat.block_size)
+                    settings=st, var_order=pat.var_order, block_size=pat.block_size)
 for r in range(repeats):
     s.setup(d["A_val"], d["l"], d["u"])
     s.set_warm_start(d["x0"])
