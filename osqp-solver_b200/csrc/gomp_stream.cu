@@ -374,6 +374,8 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                                                                   const __grid_constant__ DevStream X) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kST = NT; // threads of this instantiation (shadows the default used by the 512-thread kernel)
+    constexpr int kG = SM ? kStreamSmallGroup : kStreamGroup;         // fast path: stages per bulk copy ...
+    constexpr int kR = SM ? kStreamSmallGroupRing : kStreamGroupRing; // ... and groups in flight per chain (= X.grp, X.grp_ring)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bs = BS > 0 ? BS : S.bs;
     const int T = S.T, np = S.n_pad, mu = S.m_used, h = S.T / 2, bb = bs * bs;
@@ -771,9 +773,9 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                 // (issuing a group's bulk copies costs several hundred cycles, so the two chains get a lane each); a slot
                 // is refilled as soon as its consumer has released it ("empty" barrier).
                 if (lane < 2) {
-                    const int blkD = bs * S.ow, grpD = X.grp * (bb + blkD);
+                    const int blkD = bs * S.ow, grpD = kG * (bb + blkD);
                     const int L0 = h, L1 = T - 1 - h;
-                    const int ng0 = 2 * ((L0 + X.grp - 1) / X.grp), ng1 = 2 * ((L1 + X.grp - 1) / X.grp);
+                    const int ng0 = 2 * ((L0 + kG - 1) / kG), ng1 = 2 * ((L1 + kG - 1) / kG);
                     fence_proxy_async();
                     // lane c serves chain c.  Groups [pre, ngc) of this solve (the first `pre` were issued at the end of the
                     // previous one), then -- when another iteration is certain to follow with the same factor, i.e. no
@@ -783,21 +785,21 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                         const int c = lane;
                         const int ngc = c ? ng1 : ng0, L = c ? L1 : L0, ngh = ngc / 2;
                         const uint32_t base = c ? prod_k1 : prod_k0;
-                        const int ahead = do_info ? 0 : min(X.grp_ring, ngc);
+                        const int ahead = do_info ? 0 : min(kR, ngc);
                         for (int gq = pre; gq < ngc + ahead; ++gq) {
                             const int gi = gq < ngc ? gq : gq - ngc; // group within its solve
                             const bool first = gi < ngh;
                             const int k = first ? gi : gi - ngh;
-                            const int cnt = min(X.grp, L - k * X.grp);
+                            const int cnt = min(kG, L - k * kG);
                             int t0, dir, tbo;
                             if (c == 0) {
-                                if (first) { t0 = k * X.grp; dir = 1; tbo = -1; }
-                                else { t0 = h - 1 - k * X.grp; dir = -1; tbo = 0; }
+                                if (first) { t0 = k * kG; dir = 1; tbo = -1; }
+                                else { t0 = h - 1 - k * kG; dir = -1; tbo = 0; }
                             } else {
-                                if (first) { t0 = T - 1 - k * X.grp; dir = -1; tbo = 0; }
-                                else { t0 = h + 1 + k * X.grp; dir = 1; tbo = -1; }
+                                if (first) { t0 = T - 1 - k * kG; dir = -1; tbo = 0; }
+                                else { t0 = h + 1 + k * kG; dir = 1; tbo = -1; }
                             }
-                            const uint32_t kk = base + (uint32_t)gq, slot = kk % X.grp_ring, round = kk / X.grp_ring;
+                            const uint32_t kk = base + (uint32_t)gq, slot = kk % kR, round = kk / kR;
                             uint64_t *fullb = sFull + c * kStreamRing + slot, *emptyb = sEmpty + c * kStreamRing + slot;
                             {
                                 unsigned spins = 0; // first use of a slot: the wait on the previous phase passes at once
@@ -811,7 +813,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                             const uint32_t bytesD = (uint32_t)(cnt * bb) * 8u, bytesO = b_hi >= b_lo ? (uint32_t)((b_hi - b_lo + 1) * blkD) * 8u : 0u;
                             mbar_expect_tx(fullb, bytesD + bytesO);
                             bulk_g2s(dst, gDinv + (size_t)tlo * bb, bytesD, fullb);
-                            if (bytesO) bulk_g2s(dst + X.grp * bb + (b_lo - (tlo + tbo)) * blkD, gOff + (size_t)b_lo * blkD, bytesO, fullb);
+                            if (bytesO) bulk_g2s(dst + kG * bb + (b_lo - (tlo + tbo)) * blkD, gOff + (size_t)b_lo * blkD, bytesO, fullb);
                         }
                         pre = ahead;
                     }
@@ -874,25 +876,25 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                 };
                 const bool fast = fastp;
                 if (fast) {
-                    // ---- fast path: the factor streams in groups of X.grp stages (one bulk copy for the
+                    // ---- fast path: the factor streams in groups of kG stages (one bulk copy for the
                     // pivot-block inverses, one for the off-diagonal blocks); inside a group the hand-scheduled
                     // sweep of the resident kernel runs on the slot as if it were the resident factor
                     const int L = warp == 0 ? h : T - 1 - h; // stages of this chain
-                    const int ng = (L + X.grp - 1) / X.grp, ngroups = 2 * ng;
-                    const int blkD = bs * S.ow, grpD = X.grp * (bb + blkD);
+                    const int ng = (L + kG - 1) / kG, ngroups = 2 * ng;
+                    const int blkD = bs * S.ow, grpD = kG * (bb + blkD);
                     struct Grp { int t0, cnt, dir, tbo; bool fwd; };
                     auto group_of = [&](int gi) {
                         Grp g;
                         const bool first = gi < ng;
                         const int k = first ? gi : gi - ng;
-                        g.cnt = min(X.grp, L - k * X.grp);
+                        g.cnt = min(kG, L - k * kG);
                         g.fwd = first;
                         if (warp == 0) {
-                            if (first) { g.t0 = k * X.grp; g.dir = 1; g.tbo = -1; }
-                            else { g.t0 = h - 1 - k * X.grp; g.dir = -1; g.tbo = 0; }
+                            if (first) { g.t0 = k * kG; g.dir = 1; g.tbo = -1; }
+                            else { g.t0 = h - 1 - k * kG; g.dir = -1; g.tbo = 0; }
                         } else {
-                            if (first) { g.t0 = T - 1 - k * X.grp; g.dir = -1; g.tbo = 0; }
-                            else { g.t0 = h + 1 + k * X.grp; g.dir = 1; g.tbo = -1; }
+                            if (first) { g.t0 = T - 1 - k * kG; g.dir = -1; g.tbo = 0; }
+                            else { g.t0 = h + 1 + k * kG; g.dir = 1; g.tbo = -1; }
                         }
                         return g;
                     };
@@ -914,17 +916,18 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                             prev = sRHS[h * bs + r];
                         }
                         const Grp g = group_of(gi);
-                        const uint32_t kk = ring_k + (uint32_t)gi, slot = kk % X.grp_ring;
-                        wait_slot(slot, (kk / X.grp_ring) & 1u);
+                        const uint32_t kk = ring_k + (uint32_t)gi, slot = kk % kR;
+                        wait_slot(slot, (kk / kR) & 1u);
                         const int tlo = g.dir > 0 ? g.t0 : g.t0 - g.cnt + 1;
                         const uint32_t sl = ring0 + slot * (uint32_t)grpD * 8u;
                         const uint32_t dinv0 = sl - (uint32_t)(tlo * bb) * 8u;                                    // virtual base: stage t at + t*bb*8
-                        const uint32_t off0 = sl + (uint32_t)(X.grp * bb) * 8u - (uint32_t)(tlo + g.tbo) * blk_bytes; // block tb at + tb*blk_bytes
+                        const uint32_t off0 = sl + (uint32_t)(kG * bb) * 8u - (uint32_t)(tlo + g.tbo) * blk_bytes; // block tb at + tb*blk_bytes
                         const bool tr = g.tbo == 0;
                         prev = chain_sweep_ool<BS>(dinv0, rhs0, off0, vb0, g.t0, g.cnt, g.dir, g.tbo, T - 1, blk_bytes, g.fwd, prev, lane,
                                                tr ? tg0 : fg0, tr ? tg1 : fg1, tr ? to0 : fo0, tr ? to1 : fo1, tr ? th0 : fh0, tr ? th1 : fh1);
                         __syncwarp(); // every lane's reads of the slot have retired: hand it back to the producer warp
                         if (lane == 0) mbar_arrive(sEmpty + warp * kStreamRing + slot);
+
                     }
                     ring_k += (uint32_t)ngroups;
                 } else {
