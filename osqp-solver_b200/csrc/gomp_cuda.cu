@@ -584,6 +584,15 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
         x.ring_doubles = (grouped ? std::max(small ? 0 : kStreamRing, x.grp * x.grp_ring) : x.gen_ring) * x.slot_doubles;
         x.oRing = take(8 * (size_t)2 * x.ring_doubles);
         const int groups = 2; // factor groups: 2 x 224 threads, or 2 x 112 in the 256-thread CTAs of the small-QP mode
+        // Ruiz scratch: P values in the right-hand side region, column factors + P-side patterns in the ring region
+        x.p_scratch = ((size_t)s.nnzPu <= (size_t)s.n_pad &&
+                       8 * (size_t)s.n_pad + 4 * ((size_t)s.nnzPu + s.pf_csr.size()) + 2 * ((size_t)s.n_pad + 2) + 16 <= 8 * (size_t)2 * x.ring_doubles)
+                          ? 1 : 0;
+        x.e_scratch = 0;
+        if (x.p_scratch) {
+            const size_t used = (8 * (size_t)s.n_pad + 4 * ((size_t)s.nnzPu + s.pf_csr.size()) + 2 * ((size_t)s.n_pad + 2) + 15) & ~(size_t)15;
+            if (used + 8 * (size_t)s.m_used <= 8 * (size_t)2 * x.ring_doubles) x.e_scratch = (int)(used / 8);
+        }
         x.oPub = take(8 * (size_t)128 * groups);
         x.oDprev = take(8 * (size_t)groups * s.bs * s.bs);
         x.oOffBuf = take(8 * (size_t)groups * s.bs * std::max(1, s.ow));

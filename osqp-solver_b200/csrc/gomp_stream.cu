@@ -556,15 +556,45 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
         SMARK(PH_LOAD);
 
         // ------------------------------------------------------------------ Ruiz equilibration
+        // The P side of the scaling (values, their (i, j) positions, the full-symmetric column view) and the column
+        // factors of a pass are kept in shared memory while it runs when they fit the regions that are idle before the
+        // first iteration -- the right-hand side (P values) and the factor ring (patterns, column factors); otherwise
+        // they are read from the workspace / pattern arrays in L2.
+        const bool pscr = X.p_scratch != 0;
+        double *const Pv = pscr ? sRHS : gP;
+        double *const dtv = pscr ? sRing : gT;
+        const uint32_t *const puij = pscr ? reinterpret_cast<const uint32_t *>(sRing + np) : S.Pu_ij;
+        const uint32_t *const pfent = pscr ? puij + S.nnzPu : S.pf_csr;
+        const uint16_t *const pfptr = pscr ? reinterpret_cast<const uint16_t *>(pfent + S.npf) : S.pf_ptr;
+        // ... and the row factors E, when the ring has room behind the patterns (X.e_scratch = offset in doubles, 0 = none)
+        double *const Ev = X.e_scratch > 0 ? sRing + X.e_scratch : gE;
+        if (pscr) {
+            uint32_t *w_ij = reinterpret_cast<uint32_t *>(sRing + np), *w_ent = w_ij + S.nnzPu;
+            uint16_t *w_ptr = reinterpret_cast<uint16_t *>(w_ent + S.npf);
+            for (int k = tid; k < S.nnzPu; k += kST) {
+                Pv[k] = gP[k];
+                w_ij[k] = S.Pu_ij[k];
+            }
+            for (int k = tid; k < S.npf; k += kST) w_ent[k] = S.pf_csr[k];
+            for (int k = tid; k <= np; k += kST) w_ptr[k] = S.pf_ptr[k];
+            if (X.e_scratch > 0)
+                for (int i = tid; i < mu; i += kST) Ev[i] = 1.0;
+            __syncthreads();
+        }
+        auto pf_absmax = [&](int p_) {
+            double nrm = 0.0;
+            for (int q = pfptr[p_], q1 = pfptr[p_ + 1]; q < q1; ++q) nrm = fmax(nrm, fabs(Pv[pfent[q] & 0xFFFFu]));
+            return nrm;
+        };
         double cscale = 1.0;
 #pragma unroll 1
         for (int it = 0; it < st.scaling; ++it) {
             COLS2(p, p2, two) {
                 double na, nb;
                 col_absmax_2(p, p2, na, nb);
-                const double pa = pf_absmax_g(S, p, gP), pb = pf_absmax_g(S, p2, gP);
-                gT[p] = 1.0 / sqrt(limit_scaling(fmax(pa, na)));
-                if (two) gT[p2] = 1.0 / sqrt(limit_scaling(fmax(pb, nb)));
+                const double pa = pf_absmax(p), pb = pf_absmax(p2);
+                dtv[p] = 1.0 / sqrt(limit_scaling(fmax(pa, na)));
+                if (two) dtv[p2] = 1.0 / sqrt(limit_scaling(fmax(pb, nb)));
             }
             ROWS2(i, i2, two) {
                 double na, nb;
@@ -576,18 +606,18 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             ROWS2(i, i2, two) {
                 const double ea = gW[i], eb = gW[i2];
                 row_scale2(i, i2, two, ea, eb);
-                gE[i] *= ea;
-                if (two) gE[i2] *= eb;
+                Ev[i] *= ea;
+                if (two) Ev[i2] *= eb;
             }
 #pragma unroll 4
             for (int k = tid; k < S.nnzPu; k += kST) {
-                const uint32_t ij = __ldg(S.Pu_ij + k);
-                gP[k] = (gP[k] * gT[ij >> 16]) * gT[ij & 0xFFFFu];
+                const uint32_t ij = puij[k];
+                Pv[k] = (Pv[k] * dtv[ij >> 16]) * dtv[ij & 0xFFFFu];
             }
             __syncthreads();
             double psum = 0.0, qn[1] = {0.0};
             COLS2(p, p2, two) {
-                const double da = gT[p], db = gT[p2];
+                const double da = dtv[p], db = dtv[p2];
                 col_scale_2(p, p2, two, da, db);
                 gD[p] *= da;
                 if (two) gD[p2] *= db;
@@ -599,7 +629,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                         qn[0] = fmax(qn[0], fabs(gq[p2]));
                     }
                 }
-                const double pa = pf_absmax_g(S, p, gP), pb = pf_absmax_g(S, p2, gP);
+                const double pa = pf_absmax(p), pb = pf_absmax(p2);
                 psum += pa;
                 if (two) psum += pb;
             }
@@ -607,11 +637,16 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             block_max<1, NT>(qn, sRed, tid);
             double ct = fmax(psum / (double)S.n, limit_scaling(qn[0]));
             ct = 1.0 / limit_scaling(ct);
-            for (int k = tid; k < S.nnzPu; k += kST) gP[k] *= ct;
+            for (int k = tid; k < S.nnzPu; k += kST) Pv[k] *= ct;
             if (hasq)
                 for (int p = tid; p < np; p += kST) gq[p] *= ct;
             cscale *= ct;
             __syncthreads();
+        }
+        if (pscr) { // the scaled objective (and E) go back to the workspace (assembly, residual checks)
+            for (int k = tid; k < S.nnzPu; k += kST) gP[k] = Pv[k];
+            if (X.e_scratch > 0)
+                for (int i = tid; i < mu; i += kST) gE[i] = Ev[i];
         }
         for (int i = tid; i < mu; i += kST) {
             gLo[i] *= gE[i];

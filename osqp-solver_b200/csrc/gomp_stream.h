@@ -27,6 +27,8 @@ struct DevStream {
     int roww, colw;
     int gen_ring;      // generic path: ring slots (one stage each) per substitution warp, <= kStreamRing
     int grp, grp_ring; // fast path: stages per bulk copy, groups in flight per substitution warp
+    int e_scratch;     // ... and the row factors E behind them (offset into the ring in doubles, 0 = they stay in the workspace)
+    int p_scratch;     // the P side of the Ruiz scaling fits the idle right-hand side / ring regions (shared memory)
     int small;         // small-QP mode: A values, w and the CSR / CSC pattern arrays in shared memory, 256 threads per CTA
     int oA, oW, oRowEnt, oRowRange, oColRange, oCscRow; // ... their byte offsets
     int slot_doubles; // bs*bs + bs*ow, one ring slot
