@@ -611,17 +611,13 @@ __device__ __forceinline__ void factor_block_group(const DevSym &S, unsigned cha
             const double invdet = 1.0 / (a * d - b * c);
             const bool ik = (i >> 1) == (k >> 1), jk = (j >> 1) == (k >> 1);
             const double u1 = d * r1 - b * r2, u2 = a * r2 - c * r1; // adj(P) M_Kj
-            if (!ik && !jk) {
-                v = fma(-(c1 * u1 + c2 * u2), invdet, v);
-            } else if (ik && !jk) {
-                v = (i == k ? u1 : u2) * invdet;
-            } else if (!ik && jk) {
-                const double w1 = c1 * d - c2 * c, w2 = c2 * a - c1 * b; // M_iK adj(P)
-                v = -((j == k ? w1 : w2) * invdet);
-            } else {
-                const double adj = i == k ? (j == k ? d : -b) : (j == k ? -c : a);
-                v = adj * invdet;
-            }
+            const double w1 = c1 * d - c2 * c, w2 = c2 * a - c1 * b; // M_iK adj(P)
+            // all four cases computed, one selected: no divergent paths inside the warp
+            const double gen = fma(-(c1 * u1 + c2 * u2), invdet, v);
+            const double rowv = (i == k ? u1 : u2) * invdet;
+            const double colv = -((j == k ? w1 : w2) * invdet);
+            const double piv = (i == k ? (j == k ? d : -b) : (j == k ? -c : a)) * invdet;
+            v = ik ? (jk ? piv : rowv) : (jk ? colv : gen);
         }
         val[0] = v;
     } else

@@ -286,19 +286,13 @@ __device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dal
                 const double c1 = buf[32 + i], c2 = buf[48 + i];
                 const bool ik = (i >> 1) == (k >> 1), jk = (j >> 1) == (k >> 1);
                 const double u1 = d * r1 - b * r2, u2 = a * r2 - c * r1;
-                double v = val[q];
-                if (!ik && !jk) {
-                    v = fma(-(c1 * u1 + c2 * u2), invdet, v);
-                } else if (ik && !jk) {
-                    v = (i == k ? u1 : u2) * invdet;
-                } else if (!ik && jk) {
-                    const double w1 = c1 * d - c2 * c, w2 = c2 * a - c1 * b;
-                    v = -((j == k ? w1 : w2) * invdet);
-                } else {
-                    const double adj = i == k ? (j == k ? d : -b) : (j == k ? -c : a);
-                    v = adj * invdet;
-                }
-                val[q] = v;
+                // all four cases computed, one selected: no divergent paths inside the warp
+                const double w1 = c1 * d - c2 * c, w2 = c2 * a - c1 * b;
+                const double gen = fma(-(c1 * u1 + c2 * u2), invdet, val[q]);
+                const double rowv = (i == k ? u1 : u2) * invdet;
+                const double colv = -((j == k ? w1 : w2) * invdet);
+                const double piv = (i == k ? (j == k ? d : -b) : (j == k ? -c : a)) * invdet;
+                val[q] = ik ? (jk ? piv : rowv) : (jk ? colv : gen);
             }
         }
     } else
