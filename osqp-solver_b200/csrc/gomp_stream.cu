@@ -201,9 +201,41 @@ __device__ __forceinline__ void col_scale2(const DevSym &S, const DevStream &X, 
 // `offbuf` (shared memory, bs*ow doubles per group) stages the off-diagonal block of the Schur update.
 // GS = threads of the group (224: one matrix entry per thread for a 14 x 14 block; 128: up to two -- the 256-thread CTAs
 // of the small-QP mode run both elimination chains at once with two half-size groups).
+// Off-diagonal pattern of a thread's matrix entries (r, c), for patterns shared by every block and at most two entries per
+// block row / column: [pass 0 = block above, 1 = block below][entry][0..1] = neighbour index of r (ia) and of c (ib), -1 =
+// none, and the positions of the two values inside the staged off-diagonal block (va, vb).  Loaded once per
+// factorisation instead of once per stage (the pattern arrays live in L2).
+template <int EPL>
+struct SchurPattern {
+    signed char ia[2][EPL][2], ib[2][EPL][2];
+    short va[2][EPL][2], vb[2][EPL][2];
+    bool valid;
+};
+template <int EPL>
+__device__ __forceinline__ void load_schur_pattern(const DevSym &S, int bs, int gl, int GS, SchurPattern<EPL> &P) {
+    P.valid = S.uniform_off && S.ow <= 2 && S.owT <= 2;
+    if (!P.valid) return;
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) {
+        const int e = gl + q * GS, r = e < bs * bs ? e / bs : 0, c = e < bs * bs ? e - r * bs : 0;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            P.ia[0][q][s] = s < S.ow ? S.off_col[r * S.ow + s] : -1;
+            P.ib[0][q][s] = s < S.ow ? S.off_col[c * S.ow + s] : -1;
+            P.va[0][q][s] = (short)(r * S.ow + s);
+            P.vb[0][q][s] = (short)(c * S.ow + s);
+            P.ia[1][q][s] = s < S.owT ? S.offT_row[r * S.owT + s] : -1;
+            P.ib[1][q][s] = s < S.owT ? S.offT_row[c * S.owT + s] : -1;
+            P.va[1][q][s] = s < S.owT ? (short)S.offT_slot[r * S.owT + s] : 0;
+            P.vb[1][q][s] = s < S.owT ? (short)S.offT_slot[c * S.owT + s] : 0;
+        }
+    }
+}
+
 template <int BS, int GS>
 __device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dall, const double *Offall, double *pub, double *dprev,
-                                                    double *offbuf, bool prev_valid, int t, int mode, int g, int gl) {
+                                                    double *offbuf, bool prev_valid, int t, int mode, int g, int gl,
+                                                    const SchurPattern<(BS > 0 ? (BS * BS + GS - 1) / GS : (1024 + GS - 1) / GS)> *sp = nullptr) {
     constexpr int EPL = BS > 0 ? (BS * BS + GS - 1) / GS : (1024 + GS - 1) / GS; // entries per thread (bs <= 32)
     const int bs = BS > 0 ? BS : S.bs, nn = bs * bs;
     double *M = Dall + (size_t)t * nn;
@@ -229,6 +261,26 @@ __device__ __forceinline__ void factor_block_stream(const DevSym &S, double *Dal
         const double *blk = offbuf;
         const int tp = S.uniform_off ? 0 : tb; // pattern block (L1-resident when every block shares one pattern)
         const int cnt = above ? S.ow : S.owT;
+        if (sp != nullptr && sp->valid) {
+            const int ps = above ? 0 : 1;
+#pragma unroll
+            for (int q = 0; q < EPL; ++q) {
+                if (ri[q] < 0) continue;
+                double acc = 0.0;
+#pragma unroll
+                for (int s1 = 0; s1 < 2; ++s1) {
+                    const int a = sp->ia[ps][q][s1];
+                    if (a < 0) continue;
+                    const double va = blk[sp->va[ps][q][s1]];
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                        const int b2 = sp->ib[ps][q][s2];
+                        if (b2 >= 0) acc += va * Dn[a * bs + b2] * blk[sp->vb[ps][q][s2]];
+                    }
+                }
+                val[q] -= acc;
+            }
+        } else
 #pragma unroll
         for (int q = 0; q < EPL; ++q) {
             if (ri[q] < 0) continue;
@@ -734,23 +786,27 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                     if (tid < 2 * kHalf) {
                         const int g = tid / kHalf, gl_ = tid - g * kHalf;
                         double *pub = sPub + g * 128, *dprev = sDprev + (size_t)g * bb, *obuf = sOffBuf + (size_t)g * bs * S.ow;
+                        SchurPattern<(BS > 0 ? (BS * BS + kHalf - 1) / kHalf : (1024 + kHalf - 1) / kHalf)> spat;
+                        load_schur_pattern(S, bs, gl_, kHalf, spat);
                         if (g == 0) {
 #pragma unroll 1
-                            for (int t = 0; t < h; ++t) factor_block_stream<BS, kHalf>(S, gDinv, gOff, pub, dprev, obuf, true, t, t > 0 ? 1 : 0, 0, gl_);
+                            for (int t = 0; t < h; ++t) factor_block_stream<BS, kHalf>(S, gDinv, gOff, pub, dprev, obuf, true, t, t > 0 ? 1 : 0, 0, gl_, &spat);
                         } else {
 #pragma unroll 1
-                            for (int t = T - 1; t > h; --t) factor_block_stream<BS, kHalf>(S, gDinv, gOff, pub, dprev, obuf, true, t, t < T - 1 ? 2 : 0, 1, gl_);
+                            for (int t = T - 1; t > h; --t) factor_block_stream<BS, kHalf>(S, gDinv, gOff, pub, dprev, obuf, true, t, t < T - 1 ? 2 : 0, 1, gl_, &spat);
                         }
                     }
                 } else if (tid < 2 * kGroup) {
                     const int g = tid / kGroup, gl_ = tid - g * kGroup;
                     double *pub = sPub + g * 128, *dprev = sDprev + (size_t)g * bb, *obuf = sOffBuf + (size_t)g * bs * S.ow;
+                    SchurPattern<(BS > 0 ? (BS * BS + kGroup - 1) / kGroup : (1024 + kGroup - 1) / kGroup)> spat;
+                    load_schur_pattern(S, bs, gl_, kGroup, spat);
                     if (g == 0) {
 #pragma unroll 1
-                        for (int t = 0; t < h; ++t) factor_block_stream<BS, kGroup>(S, gDinv, gOff, pub, dprev, obuf, true, t, t > 0 ? 1 : 0, 0, gl_);
+                        for (int t = 0; t < h; ++t) factor_block_stream<BS, kGroup>(S, gDinv, gOff, pub, dprev, obuf, true, t, t > 0 ? 1 : 0, 0, gl_, &spat);
                     } else {
 #pragma unroll 1
-                        for (int t = T - 1; t > h; --t) factor_block_stream<BS, kGroup>(S, gDinv, gOff, pub, dprev, obuf, true, t, t < T - 1 ? 2 : 0, 1, gl_);
+                        for (int t = T - 1; t > h; --t) factor_block_stream<BS, kGroup>(S, gDinv, gOff, pub, dprev, obuf, true, t, t < T - 1 ? 2 : 0, 1, gl_, &spat);
                     }
                 }
                 __syncthreads();
