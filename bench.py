@@ -90,7 +90,7 @@ class ClockSampler:
 # 2 -> 107 k, 4 -> 130 k, 6 -> 142 k, 8 -> 142 k QP/s at the time; more only adds memory); every step still is a full
 # cold setup + warm start + solve.  The timed region ends with the drain of the last batches (their max_iter QPs take
 # 50 ms each), so few steps under-report the steady state: 16 steps 158 k, 24 steps 164 k QP/s.
-PIPE = int(os.environ.get("GOMP_BENCH_PIPE", "8"))
+PIPE = int(os.environ.get("GOMP_BENCH_PIPE", "12"))
 
 
 def workload(pkg):
@@ -375,7 +375,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=128)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="gomp_cuda", choices=["gomp_cuda", "reference"])
     args = ap.parse_args()

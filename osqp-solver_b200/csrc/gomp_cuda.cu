@@ -599,7 +599,7 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
         x.oV = take(8 * 128);
         x.oMid = take(8 * ((size_t)s.bs * s.bs + 2 * (size_t)s.bs * std::max(1, s.ow)));
         x.oRed = take(8 * (size_t)kRedK * ((small ? kStreamSmallThreads : kStreamThreads) / 32));
-        x.oBar = take(8 * 4 * kStreamRing + 16); // full + empty barriers of both chains, work-queue slot
+        x.oBar = take(8 * 4 * kStreamRing + 16 + 64); // full + empty barriers of both chains, work-queue slot, rho table
         x.oA = x.oW = x.oRowEnt = x.oRowRange = x.oColRange = x.oCscRow = 0;
         if (small) {
             x.oA = take(8 * (size_t)s.nnzA);
@@ -613,7 +613,8 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     };
     // small-QP mode: two 256-thread CTAs per SM, sparse data in shared memory -- when a CTA fits half an SM
     const size_t half_sm = (size_t)prop.sharedMemPerMultiprocessor / 2 - 1024;
-    const bool small_ok = s.bs % 2 == 0 && s.bs <= 32 && grouped && !std::getenv("GOMP_STREAM_NO_SMALL") && layout(true) <= half_sm;
+    const bool small_ok = s.bs % 2 == 0 && s.bs <= 32 && grouped && !std::getenv("GOMP_STREAM_NO_SMALL") && layout(true) <= half_sm &&
+                          s.m_used <= 16 * kStreamSmallThreads; // a row's rho kind: two bits of a 32-bit register per owner thread
 
     h->kernel = pick_kernel(h->sym.m_used, h->sym.n_pad, h->sym.bs);
     const bool resident_ok = h->kernel.launch && h->smem_bytes <= (size_t)prop.sharedMemPerBlockOptin;

@@ -436,6 +436,9 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
     uint64_t *const sFull = reinterpret_cast<uint64_t *>(smem_raw + X.oBar); // [2][kStreamRing] "slot filled" (bulk copies complete)
     uint64_t *const sEmpty = sFull + 2 * kStreamRing;                        // [2][kStreamRing] "slot consumed" (fast path)
     int *const sWork = reinterpret_cast<int *>(smem_raw + X.oBar + 8 * 4 * kStreamRing);
+    // small-QP mode: the three values rho takes over the rows (loose, inequality, equality) and their reciprocals; a row's
+    // kind sits in two bits of its owner's `rtype` register, so the update never fetches rho from L2 nor divides by it
+    double *const sRhoTab = reinterpret_cast<double *>(smem_raw + X.oBar + 8 * 4 * kStreamRing + 16);
 
     // per-CTA workspace (global, L2-resident)
     double *const ws = X.ws + (size_t)blockIdx.x * X.stride;
@@ -734,18 +737,33 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
         int iters_done = 0;
         double pri_res = 0.0, dua_res = 0.0;
         bool need_factor = true, w_dirty = true;
+        uint32_t rtype = 0; // small-QP mode: kind of row tid + k*kST in bits 2k, 2k+1
 
 #pragma unroll 1
         for (int iter = 1; status == -10 && iter <= st.max_iter; ++iter) {
             if (need_factor) {
                 // ---------------- rho per row, assembly of S, two-way block factorisation
                 const double rho_eq = kRhoEqOverIneq * rho;
-                for (int i = tid; i < mu; i += kST) {
+                uint32_t rt = 0;
+                for (int i = tid, kq = 0; i < mu; i += kST, kq += 2) {
                     const double lo = gLo[i], hi = gHi[i];
                     double rv = rho;
-                    if (lo < -kInfty * kMinScaling && hi > kInfty * kMinScaling) rv = kRhoMin;
-                    else if (hi - lo < kRhoTol) rv = rho_eq;
+                    uint32_t kind = 1u;
+                    if (lo < -kInfty * kMinScaling && hi > kInfty * kMinScaling) { rv = kRhoMin; kind = 0u; }
+                    else if (hi - lo < kRhoTol) { rv = rho_eq; kind = 2u; }
                     gRho[i] = rv;
+                    if (SM) rt |= kind << kq;
+                }
+                if (SM) {
+                    rtype = rt;
+                    if (tid == 0) {
+                        sRhoTab[0] = kRhoMin;
+                        sRhoTab[1] = rho;
+                        sRhoTab[2] = rho_eq;
+                        sRhoTab[4] = 1.0 / kRhoMin;
+                        sRhoTab[5] = 1.0 / rho;
+                        sRhoTab[6] = 1.0 / rho_eq;
+                    }
                 }
                 __syncthreads();
                 {
@@ -829,20 +847,48 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             }
             // ---------------- rhs = sigma x - q + A'(rho z - y)
             if (w_dirty) {
+                if constexpr (SM) {
 #pragma unroll 4
-                for (int i = tid; i < mu; i += kST) gW[i] = fma(gRho[i], gz[i], -gy[i]);
+                    for (int i = tid, kq = 0; i < mu; i += kST, kq += 2) gW[i] = fma(sRhoTab[(rtype >> kq) & 3u], gz[i], -gy[i]);
+                } else {
+#pragma unroll 4
+                    for (int i = tid; i < mu; i += kST) gW[i] = fma(gRho[i], gz[i], -gy[i]);
+                }
                 __syncthreads();
                 w_dirty = false;
             }
-            COLS2(p, p2, two) {
-                double ra = st.sigma * gx[p], rb = st.sigma * gx[p2];
-                if (hasq) {
-                    ra -= gq[p];
-                    rb -= gq[p2];
+            if constexpr (SM) {
+                // x lives in L2: the loads of four columns go out before the first gather, one round trip for all of them
+#pragma unroll 1
+                for (int p0 = tid; p0 < np; p0 += 4 * kST) {
+                    double xv[4], qv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int p = p0 + j * kST;
+                        xv[j] = p < np ? gx[p] : 0.0;
+                        qv[j] = (hasq && p < np) ? gq[p] : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int p = p0 + j * kST;
+                        if (p < np) {
+                            double ra = st.sigma * xv[j];
+                            if (hasq) ra -= qv[j];
+                            sRHS[p] = col_dot4(sColRange[p], gA, sCscRow, gW, ra);
+                        }
+                    }
                 }
-                col_dot2(p, p2, gW, ra, rb);
-                sRHS[p] = ra;
-                if (two) sRHS[p2] = rb;
+            } else {
+                COLS2(p, p2, two) {
+                    double ra = st.sigma * gx[p], rb = st.sigma * gx[p2];
+                    if (hasq) {
+                        ra -= gq[p];
+                        rb -= gq[p2];
+                    }
+                    col_dot2(p, p2, gW, ra, rb);
+                    sRHS[p] = ra;
+                    if (two) sRHS[p2] = rb;
+                }
             }
             __syncthreads();
             SMARK(PH_RHS);
@@ -1058,34 +1104,86 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             SMARK(PH_SOLVE);
 
             // ---------------- x, z, y updates
-            for (int p = tid; p < np; p += kST) {
-                const double xo = gx[p];
-                const double xn = st.alpha * sRHS[p] + (1.0 - st.alpha) * xo;
-                if (do_info && hasq) gdx[p] = xn - xo;
-                gx[p] = xn;
-            }
-            ROWS2(i, i2, two) {
-                double zta, ztb;
-                row_dot2(i, i2, sRHS, zta, ztb);
-                const double rva = gRho[i], zoa = gz[i], yoa = gy[i], loa = gLo[i], hia = gHi[i];
-                const double rvb = gRho[i2], zob = gz[i2], yob = gy[i2], lob = gLo[i2], hib = gHi[i2];
-                {
-                    const double zr = st.alpha * zta + (1.0 - st.alpha) * zoa;
-                    const double zn = fmin(fmax(zr + (1.0 / rva) * yoa, loa), hia);
-                    const double d = rva * (zr - zn), yn = yoa + d;
-                    gy[i] = yn;
-                    gz[i] = zn;
-                    gW[i] = fma(rva, zn, -yn); // w = rho z - y for the next gather
-                    if (do_info) gdy[i] = d;
+            if constexpr (SM) {
+                // the iterates live in L2 (two CTAs per SM leave no registers or shared memory for them): a thread's loads
+                // for four elements are issued before any of them is used, so one L2 round trip serves four rows
+#pragma unroll 1
+                for (int p0 = tid; p0 < np; p0 += 4 * kST) {
+                    double xo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int p = p0 + j * kST;
+                        xo[j] = p < np ? gx[p] : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int p = p0 + j * kST;
+                        if (p < np) {
+                            const double xn = st.alpha * sRHS[p] + (1.0 - st.alpha) * xo[j];
+                            if (do_info && hasq) gdx[p] = xn - xo[j];
+                            gx[p] = xn;
+                        }
+                    }
                 }
-                if (two) {
-                    const double zr = st.alpha * ztb + (1.0 - st.alpha) * zob;
-                    const double zn = fmin(fmax(zr + (1.0 / rvb) * yob, lob), hib);
-                    const double d = rvb * (zr - zn), yn = yob + d;
-                    gy[i2] = yn;
-                    gz[i2] = zn;
-                    gW[i2] = fma(rvb, zn, -yn);
-                    if (do_info) gdy[i2] = d;
+#pragma unroll 1
+                for (int i0 = tid, kq = 0; i0 < mu; i0 += 4 * kST, kq += 8) {
+                    double zo[4], yo[4], lo[4], hi[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i0 + j * kST;
+                        const bool in = i < mu;
+                        zo[j] = in ? gz[i] : 0.0;
+                        yo[j] = in ? gy[i] : 0.0;
+                        lo[j] = in ? gLo[i] : 0.0;
+                        hi[j] = in ? gHi[i] : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i0 + j * kST;
+                        if (i < mu) {
+                            const uint32_t kind = (rtype >> (kq + 2 * j)) & 3u;
+                            const double rvj = sRhoTab[kind], rinv = sRhoTab[4 + kind];
+                            const double zt = row_dot4(sRowEnt, row_range(i), gA, sRHS);
+                            const double zr = st.alpha * zt + (1.0 - st.alpha) * zo[j];
+                            const double zn = fmin(fmax(zr + rinv * yo[j], lo[j]), hi[j]);
+                            const double d = rvj * (zr - zn), yn = yo[j] + d;
+                            gy[i] = yn;
+                            gz[i] = zn;
+                            gW[i] = fma(rvj, zn, -yn); // w = rho z - y for the next gather
+                            if (do_info) gdy[i] = d;
+                        }
+                    }
+                }
+            } else {
+                for (int p = tid; p < np; p += kST) {
+                    const double xo = gx[p];
+                    const double xn = st.alpha * sRHS[p] + (1.0 - st.alpha) * xo;
+                    if (do_info && hasq) gdx[p] = xn - xo;
+                    gx[p] = xn;
+                }
+                ROWS2(i, i2, two) {
+                    double zta, ztb;
+                    row_dot2(i, i2, sRHS, zta, ztb);
+                    const double rva = gRho[i], zoa = gz[i], yoa = gy[i], loa = gLo[i], hia = gHi[i];
+                    const double rvb = gRho[i2], zob = gz[i2], yob = gy[i2], lob = gLo[i2], hib = gHi[i2];
+                    {
+                        const double zr = st.alpha * zta + (1.0 - st.alpha) * zoa;
+                        const double zn = fmin(fmax(zr + (1.0 / rva) * yoa, loa), hia);
+                        const double d = rva * (zr - zn), yn = yoa + d;
+                        gy[i] = yn;
+                        gz[i] = zn;
+                        gW[i] = fma(rva, zn, -yn); // w = rho z - y for the next gather
+                        if (do_info) gdy[i] = d;
+                    }
+                    if (two) {
+                        const double zr = st.alpha * ztb + (1.0 - st.alpha) * zob;
+                        const double zn = fmin(fmax(zr + (1.0 / rvb) * yob, lob), hib);
+                        const double d = rvb * (zr - zn), yn = yob + d;
+                        gy[i2] = yn;
+                        gz[i2] = zn;
+                        gW[i2] = fma(rvb, zn, -yn);
+                        if (do_info) gdy[i2] = d;
+                    }
                 }
             }
             __syncthreads();
