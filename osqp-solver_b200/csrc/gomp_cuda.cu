@@ -593,9 +593,17 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
             const size_t used = (8 * (size_t)s.n_pad + 4 * ((size_t)s.nnzPu + s.pf_csr.size()) + 2 * ((size_t)s.n_pad + 2) + 15) & ~(size_t)15;
             if (used + 8 * (size_t)s.m_used <= 8 * (size_t)2 * x.ring_doubles) x.e_scratch = (int)(used / 8);
         }
-        x.oPub = take(8 * (size_t)128 * groups);
-        x.oDprev = take(8 * (size_t)groups * s.bs * s.bs);
-        x.oOffBuf = take(8 * (size_t)groups * s.bs * std::max(1, s.ow));
+        // factorisation scratch (published pivot rows, previous inverse, staged off-diagonal block).  In the small-QP
+        // mode it lives inside the w = rho z - y region, which is dead while a factorisation runs (w is rebuilt after
+        // every one of them)
+        const size_t szPub = 8 * (size_t)128 * groups, szDprev = (8 * (size_t)groups * s.bs * s.bs + 15) & ~(size_t)15,
+                     szOffBuf = (8 * (size_t)groups * s.bs * std::max(1, s.ow) + 15) & ~(size_t)15;
+        const bool scratch_in_w = small && szPub + szDprev + szOffBuf <= 8 * (size_t)std::max(1, s.m_used);
+        if (!scratch_in_w) {
+            x.oPub = take(szPub);
+            x.oDprev = take(szDprev);
+            x.oOffBuf = take(szOffBuf);
+        }
         x.oV = take(8 * 128);
         x.oMid = take(8 * ((size_t)s.bs * s.bs + 2 * (size_t)s.bs * std::max(1, s.ow)));
         x.oRed = take(8 * (size_t)kRedK * ((small ? kStreamSmallThreads : kStreamThreads) / 32));
@@ -604,17 +612,24 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
         if (small) {
             x.oA = take(8 * (size_t)s.nnzA);
             x.oW = take(8 * (size_t)std::max(1, s.m_used));
+            if (scratch_in_w) {
+                x.oPub = x.oW;
+                x.oDprev = x.oPub + (int)szPub;
+                x.oOffBuf = x.oDprev + (int)szDprev;
+            }
             x.oRowEnt = take(4 * ((size_t)s.nnzA + 4));
             x.oRowRange = take(2 * ((size_t)s.m_used + 2)); // 16-bit CSR row pointers
-            x.oColRange = take(4 * (size_t)s.n_pad);
+            x.oColRange = take(2 * (size_t)s.n_pad); // 16 bits per column: first entry | length << 12
             x.oCscRow = take(2 * ((size_t)s.nnzA + 4));
         }
         return o;
     };
     // small-QP mode: two 256-thread CTAs per SM, sparse data in shared memory -- when a CTA fits half an SM
     const size_t half_sm = (size_t)prop.sharedMemPerMultiprocessor / 2 - 1024;
+    bool cols_pack = true; // 16-bit packed column ranges: first entry < 4096, at most 15 entries
+    for (uint32_t cr : s.col_range) cols_pack = cols_pack && (cr >> 8) < 4096u && (cr & 0xFFu) <= 15u;
     const bool small_ok = s.bs % 2 == 0 && s.bs <= 32 && grouped && !std::getenv("GOMP_STREAM_NO_SMALL") && layout(true) <= half_sm &&
-                          s.m_used <= 16 * kStreamSmallThreads; // a row's rho kind: two bits of a 32-bit register per owner thread
+                          cols_pack && s.m_used <= 16 * kStreamSmallThreads; // a row's rho kind: two bits of a 32-bit register per owner thread
 
     h->kernel = pick_kernel(h->sym.m_used, h->sym.n_pad, h->sym.bs);
     const bool resident_ok = h->kernel.launch && h->smem_bytes <= (size_t)prop.sharedMemPerBlockOptin;

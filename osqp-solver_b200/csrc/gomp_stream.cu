@@ -448,10 +448,14 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                  *const gOff = ws + X.wOff, *const gT = ws + X.wT, *const gLo = ws + X.wLo, *const gHi = ws + X.wHi;
 
     // small-QP mode: pattern arrays in shared memory, staged once per kernel
-    uint32_t *const sRowEnt = reinterpret_cast<uint32_t *>(smem_raw + X.oRowEnt), *const sColRange = reinterpret_cast<uint32_t *>(smem_raw + X.oColRange);
+    uint32_t *const sRowEnt = reinterpret_cast<uint32_t *>(smem_raw + X.oRowEnt);
     uint16_t *const sCscRow = reinterpret_cast<uint16_t *>(smem_raw + X.oCscRow), *const sRowPtr = reinterpret_cast<uint16_t *>(smem_raw + X.oRowRange);
+    uint16_t *const sColPk = reinterpret_cast<uint16_t *>(smem_raw + X.oColRange); // column at position p: first entry | length << 12
     // (first entry << 8 | length) of compact row i, from the 16-bit CSR pointers
     auto row_range = [&](int i) { const uint32_t a = sRowPtr[i]; return (a << 8) | ((uint32_t)sRowPtr[i + 1] - a); };
+    // the same (first entry << 8 | length) for the column at position p (the host admits this mode only when every column
+    // starts below 4096 and holds at most 15 entries)
+    auto col_range = [&](int p_) { const uint32_t a = sColPk[p_]; return ((a & 0xFFFu) << 8) | (a >> 12); };
     if (SM) {
         for (int k = tid; k < S.nnzA; k += kST) {
             sRowEnt[k] = S.row_csr[k];
@@ -461,7 +465,10 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             sRowEnt[S.nnzA + tid] = 0u; // the 4-wide entry loops may read past the last row
             sCscRow[S.nnzA + tid] = 0;
         }
-        for (int k = tid; k < np; k += kST) sColRange[k] = S.col_range[k];
+        for (int k = tid; k < np; k += kST) {
+            const uint32_t cr = S.col_range[k];
+            sColPk[k] = (uint16_t)((cr >> 8) | ((cr & 0xFFu) << 12));
+        }
         for (int k = tid; k <= mu; k += kST) sRowPtr[k] = S.row_ptr[k];
     }
     if (tid == 0) {
@@ -526,8 +533,8 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
     };
     auto col_dot2 = [&](int p1, int p2, const double *vec, double &r1, double &r2) {
         if (SM) {
-            r1 = col_dot4(sColRange[p1], gA, sCscRow, vec, r1);
-            r2 = col_dot4(sColRange[p2], gA, sCscRow, vec, r2);
+            r1 = col_dot4(col_range(p1), gA, sCscRow, vec, r1);
+            r2 = col_dot4(col_range(p2), gA, sCscRow, vec, r2);
         } else {
             col_dot_ell2(S, X, np, p1, p2, gA, vec, r1, r2);
         }
@@ -537,7 +544,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             double a[2] = {0.0, 0.0};
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
-                const uint32_t rg = sColRange[w ? p2 : p1];
+                const uint32_t rg = col_range(w ? p2 : p1);
                 for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) a[w] = fmax(a[w], fabs(gA[k]));
             }
             r1 = a[0];
@@ -551,7 +558,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
                 if (w == 1 && !two) break;
-                const uint32_t rg = sColRange[w ? p2 : p1];
+                const uint32_t rg = col_range(w ? p2 : p1);
                 const double sc = w ? s2 : s1;
                 for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) gA[k] *= sc;
             }
@@ -560,7 +567,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
         }
     };
     auto row_dot1 = [&](int i, const double *vec) { return SM ? row_dot4(sRowEnt, row_range(i), gA, vec) : row_dot_g(S, i, gA, vec); };
-    auto col_dot1 = [&](int p_, const double *vec) { return SM ? col_dot4(sColRange[p_], gA, sCscRow, vec, 0.0) : col_dot_g(S, p_, gA, vec, 0.0); };
+    auto col_dot1 = [&](int p_, const double *vec) { return SM ? col_dot4(col_range(p_), gA, sCscRow, vec, 0.0) : col_dot_g(S, p_, gA, vec, 0.0); };
 
     for (;;) {
         if (tid == 0) *sWork = atomicAdd(B.work_counter, 1);
@@ -874,7 +881,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                         if (p < np) {
                             double ra = st.sigma * xv[j];
                             if (hasq) ra -= qv[j];
-                            sRHS[p] = col_dot4(sColRange[p], gA, sCscRow, gW, ra);
+                            sRHS[p] = col_dot4(col_range(p), gA, sCscRow, gW, ra);
                         }
                     }
                 }

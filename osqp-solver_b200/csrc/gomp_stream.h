@@ -11,7 +11,7 @@ constexpr int kStreamRing = 8;      // generic path: factor slots (one stage eac
 constexpr int kStreamGroup = 8;     // fast path: stages per bulk copy (long horizons)
 constexpr int kStreamGroupRing = 3; // fast path: groups in flight per substitution warp (long horizons)
 constexpr int kStreamSmallThreads = 256; // small-QP mode: threads per CTA (two CTAs per SM)
-constexpr int kStreamSmallGroup = 4, kStreamSmallGroupRing = 2; // ... and its ring geometry
+constexpr int kStreamSmallGroup = 5, kStreamSmallGroupRing = 2; // ... and its ring geometry
 constexpr int kStreamThreads = 512; // threads per CTA of the streamed kernel
 
 struct DevStream {
