@@ -1020,22 +1020,6 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                     const int L = warp == 0 ? h : T - 1 - h; // stages of this chain
                     const int ng = (L + kG - 1) / kG, ngroups = 2 * ng;
                     const int blkD = bs * S.ow, grpD = kG * (bb + blkD);
-                    struct Grp { int t0, cnt, dir, tbo; bool fwd; };
-                    auto group_of = [&](int gi) {
-                        Grp g;
-                        const bool first = gi < ng;
-                        const int k = first ? gi : gi - ng;
-                        g.cnt = min(kG, L - k * kG);
-                        g.fwd = first;
-                        if (warp == 0) {
-                            if (first) { g.t0 = k * kG; g.dir = 1; g.tbo = -1; }
-                            else { g.t0 = h - 1 - k * kG; g.dir = -1; g.tbo = 0; }
-                        } else {
-                            if (first) { g.t0 = T - 1 - k * kG; g.dir = -1; g.tbo = 0; }
-                            else { g.t0 = h + 1 + k * kG; g.dir = 1; g.tbo = -1; }
-                        }
-                        return g;
-                    };
                     const uint32_t rhs0 = smem_u32(sRHS), vb0 = smem_u32(vb), ring0 = smem_u32(ring);
                     const uint32_t blk_bytes = (uint32_t)blkD * 8u;
                     // per-lane pattern constants: forward = row r of the block above, transposed = column r of the block below
@@ -1045,28 +1029,40 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                     const int tg0 = ub[0] >= 0 ? ub[0] : 0, tg1 = ub[1] >= 0 ? ub[1] : 0;
                     const uint32_t to0 = (uint32_t)us[0] * 8u, to1 = (uint32_t)us[1] * 8u;
                     const bool th0 = ub[0] >= 0, th1 = ub[1] >= 0;
-                    double prev = 0.0;
-                    if (ng == 0) middle();
+                    uint32_t kk = ring_k;
+                    // one phase of the chain (way in: fwd, way back: !fwd) = ng groups of up to kG stages.  Everything that
+                    // is the same for the groups of a phase (direction, which off-diagonal block a stage uses, the lane's
+                    // pattern constants) is settled before the loop; a single warp runs this, so every instruction between
+                    // two sweeps is on the critical path of the iteration.
+                    auto run_phase = [&](const bool fwd, double prev) {
+                        const bool down = (warp == 0) == fwd; // top chain walks down on its way in, the bottom chain on its way back
+                        const int dir = down ? 1 : -1, tbo = down ? -1 : 0;
+                        int t0 = warp == 0 ? (fwd ? 0 : h - 1) : (fwd ? T - 1 : h + 1);
+                        const int g0 = down ? fg0 : tg0, g1 = down ? fg1 : tg1;
+                        const uint32_t o0 = down ? fo0 : to0, o1 = down ? fo1 : to1;
+                        const bool h0 = down ? fh0 : th0, h1 = down ? fh1 : th1;
+                        int left = L;
 #pragma unroll 1
-                    for (int gi = 0; gi < ngroups; ++gi) {
-                        if (gi == ng) {
-                            middle();
-                            prev = sRHS[h * bs + r];
+                        for (int k = 0; k < ng; ++k, ++kk) {
+                            const int cnt = min(kG, left);
+                            const uint32_t slot = kk % kR;
+                            wait_slot(slot, (kk / kR) & 1u);
+                            const int tlo = down ? t0 : t0 - cnt + 1;
+                            const uint32_t sl = ring0 + slot * (uint32_t)grpD * 8u;
+                            const uint32_t dinv0 = sl - (uint32_t)(tlo * bb) * 8u;                                  // virtual base: stage t at + t*bb*8
+                            const uint32_t off0 = sl + (uint32_t)(kG * bb) * 8u - (uint32_t)(tlo + tbo) * blk_bytes; // block tb at + tb*blk_bytes
+                            prev = fwd ? chain_sweep_call<BS, true>(dinv0, rhs0, off0, vb0, t0, cnt, dir, tbo, T - 1, blk_bytes, prev, lane, g0, g1, o0, o1, h0, h1)
+                                       : chain_sweep_call<BS, false>(dinv0, rhs0, off0, vb0, t0, cnt, dir, tbo, T - 1, blk_bytes, prev, lane, g0, g1, o0, o1, h0, h1);
+                            __syncwarp(); // every lane's reads of the slot have retired: hand it back to the producer warp
+                            if (lane == 0) mbar_arrive(sEmpty + warp * kStreamRing + slot);
+                            t0 += dir * cnt;
+                            left -= cnt;
                         }
-                        const Grp g = group_of(gi);
-                        const uint32_t kk = ring_k + (uint32_t)gi, slot = kk % kR;
-                        wait_slot(slot, (kk / kR) & 1u);
-                        const int tlo = g.dir > 0 ? g.t0 : g.t0 - g.cnt + 1;
-                        const uint32_t sl = ring0 + slot * (uint32_t)grpD * 8u;
-                        const uint32_t dinv0 = sl - (uint32_t)(tlo * bb) * 8u;                                    // virtual base: stage t at + t*bb*8
-                        const uint32_t off0 = sl + (uint32_t)(kG * bb) * 8u - (uint32_t)(tlo + g.tbo) * blk_bytes; // block tb at + tb*blk_bytes
-                        const bool tr = g.tbo == 0;
-                        prev = chain_sweep_ool<BS>(dinv0, rhs0, off0, vb0, g.t0, g.cnt, g.dir, g.tbo, T - 1, blk_bytes, g.fwd, prev, lane,
-                                               tr ? tg0 : fg0, tr ? tg1 : fg1, tr ? to0 : fo0, tr ? to1 : fo1, tr ? th0 : fh0, tr ? th1 : fh1);
-                        __syncwarp(); // every lane's reads of the slot have retired: hand it back to the producer warp
-                        if (lane == 0) mbar_arrive(sEmpty + warp * kStreamRing + slot);
-
-                    }
+                        return prev;
+                    };
+                    run_phase(true, 0.0);
+                    middle();
+                    run_phase(false, ng > 0 ? sRHS[h * bs + r] : 0.0);
                     ring_k += (uint32_t)ngroups;
                 } else {
                     // ---- generic path: one ring slot per stage
