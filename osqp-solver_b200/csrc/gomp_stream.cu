@@ -1005,7 +1005,33 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                         if (two_chains) named_bar_sync(1, 64);
                         Step sp;
                         sp.t = h; sp.ob = h - 1; sp.kind = 2;
-                        substep(sp, sMid, sMid + bb, sMid + bb + bs * S.ow, vb);
+                        if (fastp) {
+                            // uniform pattern: the lane's neighbour indices are in registers (ua / ub / us), nothing of the
+                            // middle stage is fetched from the pattern arrays in L2
+                            const double *Oa = sMid + bb, *Ot = sMid + bb + bs * S.ow;
+                            double a = sRHS[h * bs + r];
+                            if (h > 0) {
+                                const double *src = sRHS + (h - 1) * bs;
+#pragma unroll
+                                for (int s = 0; s < kMaxW; ++s)
+                                    if (ua[s] >= 0) a = fma(-Oa[r * S.ow + s], src[ua[s]], a);
+                            }
+                            if (h < T - 1) {
+                                const double *src = sRHS + (h + 1) * bs;
+#pragma unroll
+                                for (int s = 0; s < kMaxW; ++s)
+                                    if (ub[s] >= 0) a = fma(-Ot[us[s]], src[ub[s]], a);
+                            }
+                            if (half == 0 && rowact) vb[r] = a;
+                            __syncwarp();
+                            double acc = 0.0;
+                            for (int c = c0; c < c1; ++c) acc = fma(sMid[r * bs + c], vb[c], acc);
+                            if (halves == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                            if (half == 0 && rowact) sRHS[h * bs + r] = acc;
+                            __syncwarp();
+                        } else {
+                            substep(sp, sMid, sMid + bb, sMid + bb + bs * S.ow, vb);
+                        }
                         if (two_chains) named_bar_sync(2, 64);
                     } else if (two_chains) {
                         named_bar_sync(1, 64);
