@@ -148,8 +148,19 @@ def run_gpu(args):
     rank, local_rank, world = rank_env()
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not precede the JSON line on stdout
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner with printf when the communicator is created: keep it off stdout, which carries
+        # the one JSON line (fd 1 points at stderr until the communicator exists)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     pkg = entry.load_package()
     S = pkg.solver
     if S.device_count() < 1:
