@@ -387,8 +387,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=128)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--impl", default="gomp_cuda", choices=["gomp_cuda", "reference"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

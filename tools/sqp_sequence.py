@@ -25,7 +25,8 @@ d = P.generate(pat, 0, batch)
 
 
 def make(dev_arrays, stream):
-    st = S.default_settings(borrow_inputs=1)
+    # GOMP_SQP_THROUGHPUT=1: two QPs per SM (streamed kernel, small-QP mode) instead of the resident kernel
+    st = S.default_settings(borrow_inputs=1, prefer_throughput=int(os.environ.get("GOMP_SQP_THROUGHPUT", "0")))
     st.stream = stream.cuda_stream
     s = S.BatchQPSolver(pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx, dev_arrays["A_val"],
                         dev_arrays["l"], dev_arrays["u"], batch=batch, settings=st, var_order=pat.var_order, block_size=pat.block_size)
