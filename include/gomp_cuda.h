@@ -93,9 +93,12 @@ typedef struct gomp_settings {
     const int64_t *var_order;      /* n entries: position p holds variable var_order[p]; NULL = detect */
     int32_t threads_per_cta;       /* 0 = auto */
     int32_t borrow_inputs;         /* 1: device-pointer inputs are used in place (caller keeps them alive until the next setup/update) */
-    int32_t prefer_throughput;     /* 1 (with linsys = AUTO): when the QP also fits the two-CTAs-per-SM mode of the streamed back end,
-                                      use it -- +5..8 % QPs/s when several batches are kept in flight, but one QP alone takes
-                                      1.6x longer, so a single batch with a few max_iter problems finishes later.  0: resident kernel. */
+    int32_t prefer_throughput;     /* 1 (with linsys = AUTO): when the QP also fits the two-CTAs-per-SM mode of the streamed back end
+                                      (block size 14 with the uniform 2-wide off-diagonal pattern, < 113 KB of shared memory per
+                                      QP, at most 4096 non-empty rows, columns of at most 15 entries starting below entry 4096,
+                                      batch >= 2 QPs per SM), use it -- +40 % QPs/s on 4096 x (N=7, H=50) when several batches are
+                                      kept in flight, but one QP alone takes 1.4x longer, so a single batch with a few max_iter
+                                      problems (an SQP round sequence) finishes later.  0: resident kernel. */
 } gomp_settings;
 
 typedef struct gomp_info {
