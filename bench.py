@@ -87,9 +87,10 @@ class ClockSampler:
 
 
 # batches in flight per GPU: consecutive steps rotate over PIPE solver handles / streams (measured on B200:
-# 2 -> 107 k, 4 -> 130 k, 6 -> 142 k, 8 -> 142 k QP/s at the time; more only adds memory); every step still is a full
-# cold setup + warm start + solve.  The timed region ends with the drain of the last batches (their max_iter QPs take
-# 50 ms each), so few steps under-report the steady state: 16 steps 158 k, 24 steps 164 k QP/s.
+# 2 -> 107 k, 4 -> 130 k, 6 -> 142 k, 8 -> 142 k QP/s with the resident kernel; final build, two QPs per SM, 256 steps:
+# 12 -> 241.5 k, 16 -> 241.4 k, 24 -> 241.6 k -- more only adds memory); every step still is a full cold setup + warm
+# start + solve.  The timed region ends with the drain of the last batches (their max_iter QPs take 70 ms each), so
+# few steps under-report the steady state: 32 steps 197 k, 128 steps 213 k on one build; 64 -> 233 k, 256 -> 241 k now.
 PIPE = int(os.environ.get("GOMP_BENCH_PIPE", "12"))
 
 
