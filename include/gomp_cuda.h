@@ -62,6 +62,11 @@ extern "C" {
                                          through shared memory with TMA (long horizons: H = 400, the reference example's 802) */
 #define GOMP_LINSYS_PCG 3             /* reserved: not built (an inexact solve would change OSQP's iteration counts);
                                          gomp_batch_create returns GOMP_ERR_UNSUPPORTED */
+#define GOMP_LINSYS_BLOCKTRI_TMEM 4   /* same factorisation, TWO QPs resident per SM: one 576-thread CTA with two independent
+                                         slots, the inverted pivot blocks of both QPs kept in tensor memory (tcgen05.st / ld,
+                                         lane-private), the block factorisation inside the substitution warps.  Block size
+                                         14 or 12 with the uniform 2-wide off-diagonal pattern, 4..63 stages; AUTO picks it
+                                         whenever the QP qualifies */
 
 typedef struct gomp_batch gomp_batch;
 
@@ -105,6 +110,8 @@ typedef struct gomp_info {
     int64_t batch, n, m, m_used, nnzA, nnzP;
     int32_t block_size, num_blocks, offdiag_width;
     int32_t linsys, threads_per_cta, ctas_per_sm, num_sms, grid;
+    int32_t qps_per_sm;            /* QPs resident per SM (two slots per CTA on the TMEM back end) */
+    int32_t reserved0;
     int64_t smem_bytes;            /* dynamic shared memory per CTA */
     int64_t workspace_bytes;       /* device memory owned by the handle */
     int64_t kernel_launches;       /* launches issued by this handle so far */

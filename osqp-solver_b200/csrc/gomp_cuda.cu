@@ -24,6 +24,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <thread>
@@ -34,6 +35,7 @@
 #include <vector>
 
 #include "gomp_kernel.cuh"
+#include "gomp_duo.h"
 #include "gomp_stream.h"
 #include "symbolic.h"
 
@@ -185,6 +187,14 @@ struct gomp_batch {
     KernelChoice kernel;
     bool streamed = false; // long-horizon back end (gomp_stream.cu): QP and factor in a global workspace
     DevStream dx;
+    bool duo = false;      // two-slot back end (gomp_duo.cu): two QPs per SM, factor in tensor memory
+    DevDuo dd;
+    gomp::OwnerEll oell;
+    gomp::AssemblyEll aell;
+    DevArray<unsigned long long> d_ascon, d_asocon;
+    DevArray<uint32_t> d_asmeta, d_asometa;
+    DevArray<uint32_t> d_rell, d_cell, d_pell;
+    DevArray<uint16_t> d_cpos;
     DevArray<double> d_ws;
     DevArray<uint32_t> d_row_ell;
     DevArray<uint16_t> d_col_ell;
@@ -493,6 +503,8 @@ int gomp_batch_destroy(gomp_batch *h) {
     h->d_A.release(); h->d_l.release(); h->d_u.release(); h->d_q.release(); h->d_x0.release(); h->d_xs.release();
     h->d_zs.release(); h->d_ys.release(); h->d_rho.release(); h->d_E.release(); h->d_D.release(); h->d_qs.release(); h->d_dx.release(); h->d_Lg.release(); h->d_Ug.release(); h->d_tri_rc.release(); h->d_dy.release(); h->d_xo.release();
     h->d_yo.release(); h->d_pri.release(); h->d_dua.release(); h->d_obj.release();
+    h->d_rell.release(); h->d_cell.release(); h->d_pell.release(); h->d_cpos.release();
+    h->d_ascon.release(); h->d_asocon.release(); h->d_asmeta.release(); h->d_asometa.release();
     h->d_active.release(); h->d_order.release(); h->d_ws.release(); h->d_row_ell.release(); h->d_col_ell.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -519,7 +531,7 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     if (st.linsys == GOMP_LINSYS_PCG)
         return fail(GOMP_ERR_UNSUPPORTED, "the PCG back end is not built: long horizons use the exact streamed block-tridiagonal "
                                           "factorisation (GOMP_LINSYS_BLOCKTRI_GLOBAL), which keeps OSQP's iteration counts");
-    if (st.linsys < GOMP_LINSYS_AUTO || st.linsys > GOMP_LINSYS_PCG) return fail(GOMP_ERR_INVALID_ARGUMENT, "unknown linsys");
+    if (st.linsys < GOMP_LINSYS_AUTO || st.linsys > GOMP_LINSYS_BLOCKTRI_TMEM) return fail(GOMP_ERR_INVALID_ARGUMENT, "unknown linsys");
 
     gomp_batch *h = new gomp_batch();
     h->st = st;
@@ -631,12 +643,98 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     const bool small_ok = s.bs % 2 == 0 && s.bs <= 32 && grouped && !std::getenv("GOMP_STREAM_NO_SMALL") && layout(true) <= half_sm &&
                           cols_pack && s.m_used <= 16 * kStreamSmallThreads; // a row's rho kind: two bits of a 32-bit register per owner thread
 
+    // ---- two-slot back end (gomp_duo.cu): eligibility and shared-memory layout
+    std::string duo_why;
+    size_t duo_smem = 0;
+    {
+        DevDuo &dd = h->dd;
+        const int hmid = s.T / 2;
+        gomp::build_owner_ell(s, kDuoOwners, h->oell);
+        const gomp::OwnerEll &oe = h->oell;
+        if (!(h->ds.uniform_off && s.ow <= 2 && s.owT <= 2)) duo_why = "off-diagonal blocks are not uniform with at most two entries per row and column";
+        else if (s.T < 4 || (hmid + 1) * 16 > kDuoTmemCols) duo_why = "needs 4 <= number of stages <= 63 (one TMEM column group per stage and chain)";
+        else if (oe.rpt > kDuoMaxRpt || oe.cpt > kDuoMaxCpt || !duo_variant_exists(oe.rpt, oe.cpt, s.bs)) duo_why = "no kernel variant for this block size / rows per owner";
+        else if (*std::max_element(oe.plen.begin(), oe.plen.end()) > 4 || (s.nnzPu + kDuoOwners - 1) / kDuoOwners > 4)
+            duo_why = "P has more than 4 entries per column or more than 4 per owner thread (register-held P patterns)";
+        else if (s.nnzA > 8190 || s.m_used > 8189 || s.n_pad > 8189 || s.nnzPu > 8190) duo_why = "more than 8190 entries / rows / variables (16-bit byte offsets)";
+        else {
+            dd.rpt = oe.rpt; dd.cpt = oe.cpt;
+            for (int j = 0; j < kDuoMaxRpt; ++j) { dd.rlen[j] = j < oe.rpt ? oe.rlen[j] : 0; dd.rbase[j] = j < oe.rpt ? oe.rbase[j] * kDuoOwners * 4 : 0; } // (byte offset of the slot's first entry line)
+            for (int c = 0; c < kDuoMaxCpt; ++c) {
+                dd.clen[c] = c < oe.cpt ? oe.clen[c] : 0; dd.cbase[c] = c < oe.cpt ? oe.cbase[c] * kDuoOwners * 4 : 0;
+                dd.plen[c] = c < oe.cpt ? oe.plen[c] : 0; dd.pbase[c] = c < oe.cpt ? oe.pbase[c] * kDuoOwners : 0;
+            }
+            dd.n_row_ell = (int)oe.row_ell.size(); dd.n_col_ell = (int)oe.col_ell.size();
+            size_t o2 = 0;
+            auto take2 = [&o2](size_t bytes) {
+                size_t at = o2;
+                o2 += (bytes + 15) & ~(size_t)15;
+                return (int)at;
+            };
+            dd.oRowEll = take2(4 * oe.row_ell.size());
+            dd.oColEll = take2(4 * oe.col_ell.size());
+            dd.slot_base = (int)o2;
+            const size_t mu1 = (size_t)std::max(1, s.m_used);
+            auto slot_layout = [&](bool dedicated) {
+                o2 = 0;
+                dd.oA = take2(8 * ((size_t)s.nnzA + 2));
+                dd.oP = take2(8 * ((size_t)s.nnzPu + 2));
+                dd.oW = take2(8 * (mu1 + 2));
+                dd.oRHS = take2(8 * ((size_t)s.n_pad + 2));
+                dd.oLo = take2(8 * mu1);
+                dd.oHi = take2(8 * mu1);
+                dd.oOff = take2(8 * (size_t)std::max(1, h->ds.noff));
+                dd.oV = take2(512);
+                dd.oRed = take2(8 * (size_t)kRedK * (kDuoOwners / 32));
+                dd.oCtl = take2(128); // control word, work slot, mbarrier, cost scale, rho tables
+                if (dedicated) {
+                    dd.oScr = take2(duo_scratch_bytes(s.bs));
+                    dd.oRing = take2(duo_ring_bytes(s.bs));
+                } else { // the factorisation scratch and the S staging ring share the right-hand side region (dead while factoring)
+                    dd.oScr = dd.oRHS;
+                    dd.oRing = dd.oRHS + (int)((duo_scratch_bytes(s.bs) + 15) & ~(size_t)15);
+                }
+                dd.slot_bytes = (int)o2;
+                return (size_t)dd.slot_base + (size_t)kDuoSlots * o2;
+            };
+            duo_smem = slot_layout(true);
+            if (duo_smem > (size_t)prop.sharedMemPerBlockOptin) {
+                const bool alias_ok = ((duo_scratch_bytes(s.bs) + 15) & ~(size_t)15) + duo_ring_bytes(s.bs) <= 8 * (size_t)s.n_pad;
+                duo_smem = slot_layout(false);
+                if (!alias_ok || duo_smem > (size_t)prop.sharedMemPerBlockOptin)
+                    duo_why = "two QPs do not fit the shared memory of one SM (" + std::to_string(duo_smem) + " bytes needed)";
+            }
+        }
+    }
+    const bool duo_ok = duo_why.empty();
+    if (st.linsys == GOMP_LINSYS_BLOCKTRI_TMEM && !duo_ok) return bail(fail(GOMP_ERR_UNSUPPORTED, "two-slot TMEM back end: " + duo_why));
+    h->duo = st.linsys == GOMP_LINSYS_BLOCKTRI_TMEM || (st.linsys == GOMP_LINSYS_AUTO && duo_ok && !std::getenv("GOMP_NO_DUO"));
+
     h->kernel = pick_kernel(h->sym.m_used, h->sym.n_pad, h->sym.bs);
     const bool resident_ok = h->kernel.launch && h->smem_bytes <= (size_t)prop.sharedMemPerBlockOptin;
-    h->streamed = st.linsys == GOMP_LINSYS_BLOCKTRI_GLOBAL ||
-                  (st.linsys == GOMP_LINSYS_AUTO && (!resident_ok || (st.prefer_throughput && small_ok && batch >= 2 * (int64_t)h->num_sms)));
+    h->streamed = !h->duo && (st.linsys == GOMP_LINSYS_BLOCKTRI_GLOBAL ||
+                              (st.linsys == GOMP_LINSYS_AUTO && (!resident_ok || (st.prefer_throughput && small_ok && batch >= 2 * (int64_t)h->num_sms))));
     int occ = 0;
-    if (!h->streamed) {
+    if (h->duo) {
+        h->smem_bytes = duo_smem;
+        cudaError_t e = prepare_duo(h->dd.rpt, h->dd.cpt, s.bs, h->smem_bytes, &occ);
+        if (e != cudaSuccess) return bail(fail(GOMP_ERR_CUDA, std::string("kernel preparation failed: ") + cudaGetErrorString(e)));
+        if (occ < 1) return bail(fail(GOMP_ERR_CUDA, "kernel cannot be resident (occupancy 0)"));
+        occ = 1; // the CTA owns the SM's whole tensor memory
+        if (h->d_rell.upload(h->oell.row_ell) != cudaSuccess || h->d_cell.upload(h->oell.col_ell) != cudaSuccess ||
+            h->d_pell.upload(h->oell.pf_ell) != cudaSuccess || h->d_cpos.upload(h->oell.col_pos) != cudaSuccess)
+            return bail(fail(GOMP_ERR_ALLOC, "cudaMalloc failed for the owner ELL views"));
+        h->dd.row_ell = h->d_rell.p; h->dd.col_ell = h->d_cell.p; h->dd.pf_ell = h->d_pell.p; h->dd.col_pos = h->d_cpos.p;
+        gomp::build_assembly_ell(s, kDuoOwners, h->aell);
+        {
+            std::vector<unsigned long long> c1(h->aell.con.begin(), h->aell.con.end()), c2(h->aell.ocon.begin(), h->aell.ocon.end());
+            if (h->d_ascon.upload(c1) != cudaSuccess || h->d_asocon.upload(c2) != cudaSuccess || h->d_asmeta.upload(h->aell.meta) != cudaSuccess ||
+                h->d_asometa.upload(h->aell.ometa) != cudaSuccess)
+                return bail(fail(GOMP_ERR_ALLOC, "cudaMalloc failed for the assembly lists"));
+        }
+        h->dd.as_con = h->d_ascon.p; h->dd.as_ocon = h->d_asocon.p; h->dd.as_meta = h->d_asmeta.p; h->dd.as_ometa = h->d_asometa.p;
+        h->dd.as_ept = h->aell.ept; h->dd.as_maxc = h->aell.maxc; h->dd.as_opt = h->aell.opt; h->dd.as_maxco = h->aell.maxco;
+    } else if (!h->streamed) {
         if (!h->kernel.launch)
             return bail(fail(GOMP_ERR_UNSUPPORTED, "problem too large for the register-resident kernel (non-empty rows <= 3584, variables <= 1792)"));
         if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
@@ -772,7 +870,8 @@ int gomp_batch_solve(gomp_batch *h) {
     b.order = h->order_valid ? h->d_order.p : nullptr;
     CUDA_TRY(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    if (h->streamed) CUDA_TRY(launch_stream(h->ds, h->db, h->dst, h->dx, h->grid, h->smem_bytes, h->stream));
+    if (h->duo) CUDA_TRY(launch_duo(h->dd.rpt, h->dd.cpt, s.bs, h->ds, h->db, h->dst, h->dd, h->grid, h->smem_bytes, h->stream));
+    else if (h->streamed) CUDA_TRY(launch_stream(h->ds, h->db, h->dst, h->dx, h->grid, h->smem_bytes, h->stream));
     else CUDA_TRY(h->kernel.launch(h->ds, h->db, h->dst, h->grid, h->smem_bytes, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     // queue order of the next solve, should it be a warm re-solve of the same problems (gomp_batch_update)
@@ -907,7 +1006,10 @@ int gomp_batch_info(gomp_batch *h, gomp_info *info) {
     const gomp::Symbolic &s = h->sym;
     info->batch = h->batch; info->n = s.n; info->m = s.m; info->m_used = s.m_used; info->nnzA = s.nnzA; info->nnzP = s.nnzPu;
     info->block_size = s.bs; info->num_blocks = s.T; info->offdiag_width = s.ow;
-    info->linsys = h->streamed ? GOMP_LINSYS_BLOCKTRI_GLOBAL : GOMP_LINSYS_BLOCKTRI_SMEM; info->threads_per_cta = h->streamed ? (h->dx.small ? kStreamSmallThreads : kStreamThreads) : kThreads; info->ctas_per_sm = h->ctas_per_sm;
+    info->linsys = h->duo ? GOMP_LINSYS_BLOCKTRI_TMEM : (h->streamed ? GOMP_LINSYS_BLOCKTRI_GLOBAL : GOMP_LINSYS_BLOCKTRI_SMEM);
+    info->threads_per_cta = h->duo ? kDuoThreads : (h->streamed ? (h->dx.small ? kStreamSmallThreads : kStreamThreads) : kThreads);
+    info->ctas_per_sm = h->ctas_per_sm;
+    info->qps_per_sm = h->duo ? kDuoSlots : h->ctas_per_sm;
     info->num_sms = h->num_sms; info->grid = h->grid; info->smem_bytes = (int64_t)h->smem_bytes;
     info->workspace_bytes = (int64_t)h->workspace_bytes; info->kernel_launches = h->launches;
     float ms = 0;

@@ -160,13 +160,12 @@ inline bool analyse(Symbolic &sym, int64_t n, int64_t m, const int64_t *Pp, cons
     }
     sym.row_compact.assign((size_t)m, -1);
     for (int64_t i = 0; i < m; ++i) {
-        if (row_cnt[(size_t)i] > 0) {
-            sym.row_compact[(size_t)i] = (int32_t)sym.used_rows.size();
-            sym.used_rows.push_back((int32_t)i);
-        } else {
-            sym.empty_rows.push_back((int32_t)i);
-        }
+        if (row_cnt[(size_t)i] > 0) sym.used_rows.push_back((int32_t)i);
+        else sym.empty_rows.push_back((int32_t)i);
     }
+    // compact order: longest rows first (stable), so that rows a kernel processes side by side have similar lengths
+    std::stable_sort(sym.used_rows.begin(), sym.used_rows.end(), [&](int32_t a, int32_t b) { return row_cnt[(size_t)a] > row_cnt[(size_t)b]; });
+    for (size_t c = 0; c < sym.used_rows.size(); ++c) sym.row_compact[(size_t)sym.used_rows[c]] = (int32_t)c;
     sym.m_used = (int)sym.used_rows.size();
     if (sym.m_used > 65535) return sym.error = "more than 65535 non-empty rows", false;
 
@@ -444,6 +443,168 @@ inline bool analyse(Symbolic &sym, int64_t n, int64_t m, const int64_t *Pp, cons
     flatten(dcon, sym.sd_ptr, sym.sd_con);
     flatten(ocon, sym.so_ptr, sym.so_con);
     return true;
+}
+
+// ---- owner-thread ELL views (gomp_duo.cu) ---------------------------------------------------------------
+// The two-slot kernel gives every constraint row and every variable position a fixed owner thread out of
+// `owners`.  Rows: compact row i belongs to thread i % owners, slot j = i / owners.  Columns: positions are
+// sorted by descending entry count and dealt out the same way (col_pos), so that the columns one slot holds
+// have similar lengths.  For every slot the entries of all its rows / columns are stored "ELL by slot":
+// entry e of the row thread `oid` owns in slot j sits at row_ell[(rbase[j] + e) * owners + oid] -- one
+// coalesced, conflict-free load per step, uniform trip counts (rlen[j]) for the whole CTA, no per-row ranges.
+// Surplus entries point at zero elements the kernel keeps behind its arrays (value index nnzA / nnzPu,
+// position n_pad, row m_used).  Both halves of an entry are stored as BYTE offsets (index * 8), so the kernel adds
+// them to a base address without shifting: needs nnzA, m_used, n_pad <= 8190.
+struct OwnerEll {
+    int owners = 0, rpt = 0, cpt = 0;
+    std::vector<int> rlen, rbase, clen, cbase, plen, pbase;
+    std::vector<uint32_t> row_ell; // (8 pos << 16 | 8 k)
+    std::vector<uint32_t> col_ell; // (8 compact row << 16 | 8 k)
+    std::vector<uint32_t> pf_ell;  // (8 other pos << 16 | 8 kPu), full-symmetric view of P
+    std::vector<uint16_t> col_pos; // [cpt * owners] position owned by (slot c, thread oid), 0xFFFF = none
+};
+
+inline void build_owner_ell(const Symbolic &s, int owners, OwnerEll &o) {
+    o = OwnerEll();
+    o.owners = owners;
+    o.rpt = std::max(1, (s.m_used + owners - 1) / owners);
+    o.cpt = std::max(1, (s.n_pad + owners - 1) / owners);
+    // rows
+    int base = 0;
+    for (int j = 0; j < o.rpt; ++j) {
+        int len = 0;
+        for (int i = j * owners; i < std::min(s.m_used, (j + 1) * owners); ++i) len = std::max(len, (int)(s.row_range[(size_t)i] & 0xFFu));
+        o.rlen.push_back(len);
+        o.rbase.push_back(base);
+        base += len;
+    }
+    auto pk = [](uint32_t hi, uint32_t lo) { return ((hi * 8u) << 16) | (lo * 8u); };
+    o.row_ell.assign((size_t)std::max(1, base) * owners, pk((uint32_t)s.n_pad, (uint32_t)s.nnzA));
+    for (int i = 0; i < s.m_used; ++i) {
+        const int j = i / owners, oid = i % owners;
+        const uint32_t rr = s.row_range[(size_t)i];
+        for (uint32_t e = 0; e < (rr & 0xFFu); ++e) {
+            const uint32_t en = s.row_csr[(rr >> 8) + e];
+            o.row_ell[(size_t)(o.rbase[(size_t)j] + (int)e) * owners + oid] = pk(en >> 16, en & 0xFFFFu);
+        }
+    }
+    // columns: sort positions by (entries of A, entries of P) descending
+    std::vector<int> order((size_t)s.n_pad);
+    for (int p = 0; p < s.n_pad; ++p) order[(size_t)p] = p;
+    auto alen = [&](int p) { return (int)(s.col_range[(size_t)p] & 0xFFu); };
+    auto plen = [&](int p) { return (int)s.pf_ptr[(size_t)p + 1] - (int)s.pf_ptr[(size_t)p]; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (alen(a) != alen(b)) return alen(a) > alen(b);
+        return plen(a) > plen(b);
+    });
+    o.col_pos.assign((size_t)o.cpt * owners, 0xFFFF);
+    int cb = 0, pb = 0;
+    for (int c = 0; c < o.cpt; ++c) {
+        int la = 0, lp = 0;
+        for (int q = c * owners; q < std::min(s.n_pad, (c + 1) * owners); ++q) {
+            o.col_pos[(size_t)q] = (uint16_t)order[(size_t)q];
+            la = std::max(la, alen(order[(size_t)q]));
+            lp = std::max(lp, plen(order[(size_t)q]));
+        }
+        o.clen.push_back(la);
+        o.cbase.push_back(cb);
+        o.plen.push_back(lp);
+        o.pbase.push_back(pb);
+        cb += la;
+        pb += lp;
+    }
+    o.col_ell.assign((size_t)std::max(1, cb) * owners, pk((uint32_t)s.m_used, (uint32_t)s.nnzA));
+    o.pf_ell.assign((size_t)std::max(1, pb) * owners, pk((uint32_t)s.n_pad, (uint32_t)s.nnzPu));
+    for (int q = 0; q < s.n_pad; ++q) {
+        const int c = q / owners, oid = q % owners, p = order[(size_t)q];
+        const uint32_t cr = s.col_range[(size_t)p];
+        for (uint32_t e = 0; e < (cr & 0xFFu); ++e) {
+            const uint32_t k = (cr >> 8) + e;
+            o.col_ell[(size_t)(o.cbase[(size_t)c] + (int)e) * owners + oid] = pk((uint32_t)s.csc_row[k], k);
+        }
+        for (int e = 0; e < plen(p); ++e) {
+            const uint32_t en = s.pf_csr[(size_t)s.pf_ptr[(size_t)p] + e];
+            o.pf_ell[(size_t)(o.pbase[(size_t)c] + e) * owners + oid] = pk(en >> 16, en & 0xFFFFu);
+        }
+    }
+}
+
+// ---- assembly lists "ELL by owner" (gomp_duo.cu) ------------------------------------------------------------
+// The two-slot kernel assembles S one factorisation round at a time: round R holds stage R of the down chain and
+// stage T-1-R of the up chain (round h = T/2: the middle stage), 2 * dpb packed entries dealt out to the owner
+// threads (entry e -> thread e % owners, pass e / owners).  For every (round, pass, thread) the contributions
+//   rho[row] * A[k1] * A[k2]
+// are stored as 64-bit words (8 row | 8 k1 << 16 | 8 k2 << 32) at con[((round * ept + pass) * maxc + k) * owners + thread]
+// -- coalesced loads with a uniform trip count, no pointer chasing; surplus words multiply zeros (row m_used, value
+// index nnzA).  meta[(round * ept + pass) * owners + thread] = 8 kPu (or 8 nnzPu: none) | kind << 16 | valid << 18.
+// The off-diagonal blocks are assembled once per factorisation the same way (ocon / ometa, entry e of the ELL
+// off-diagonal storage -> thread e % owners, pass e / owners).
+struct AssemblyEll {
+    int owners = 0, rounds = 0, ept = 0, maxc = 0, opt = 0, maxco = 0;
+    std::vector<uint64_t> con, ocon;
+    std::vector<uint32_t> meta, ometa;
+};
+
+inline void build_assembly_ell(const Symbolic &s, int owners, AssemblyEll &a) {
+    a = AssemblyEll();
+    a.owners = owners;
+    const int T = s.T, h = T / 2, dpb = s.dpb;
+    a.rounds = h + 1;
+    a.ept = (2 * dpb + owners - 1) / owners;
+    auto word = [](uint32_t row, uint32_t k1, uint32_t k2) { return (uint64_t)(row * 8u) | ((uint64_t)(k1 * 8u) << 16) | ((uint64_t)(k2 * 8u) << 32); };
+    const uint64_t padw = word((uint32_t)s.m_used, (uint32_t)s.nnzA, (uint32_t)s.nnzA);
+    auto entry_of = [&](int R, int e, int &ge) { // global packed entry of local entry e of round R, false if none
+        const int nb = R == h ? 1 : (R < T - 1 - h ? 2 : 1);
+        if (e >= nb * dpb) return false;
+        const int which = e >= dpb ? 1 : 0, le = e - which * dpb;
+        ge = (which == 0 ? R : T - 1 - R) * dpb + le;
+        return true;
+    };
+    for (int R = 0; R < a.rounds; ++R)
+        for (int e = 0; e < a.ept * owners; ++e) {
+            int ge;
+            if (entry_of(R, e, ge)) a.maxc = std::max(a.maxc, (int)(s.sd_ptr[(size_t)ge + 1] - s.sd_ptr[(size_t)ge]));
+        }
+    a.maxc = std::max(a.maxc, 1);
+    a.con.assign((size_t)a.rounds * a.ept * a.maxc * owners, padw);
+    a.meta.assign((size_t)a.rounds * a.ept * owners, (uint32_t)s.nnzPu * 8u);
+    for (int R = 0; R < a.rounds; ++R)
+        for (int w = 0; w < a.ept; ++w)
+            for (int oid = 0; oid < owners; ++oid) {
+                int ge;
+                if (!entry_of(R, oid + w * owners, ge)) continue;
+                const size_t base = ((size_t)(R * a.ept + w) * a.maxc) * owners + oid;
+                uint32_t k = 0;
+                for (uint32_t q = s.sd_ptr[(size_t)ge]; q < s.sd_ptr[(size_t)ge + 1]; ++q, ++k) {
+                    const Contrib &c = s.sd_con[q];
+                    a.con[base + (size_t)k * owners] = word(c.row, c.k1, c.k2);
+                }
+                const int t = ge / dpb, le = ge - t * dpb;
+                int r = 0;
+                while ((r + 1) * (r + 2) / 2 <= le) ++r;
+                const int cc = le - r * (r + 1) / 2;
+                const uint32_t kind = r == cc ? (s.pos_var[(size_t)t * s.bs + r] < 0 ? 2u : 1u) : 0u;
+                const uint32_t pk = s.sd_pk[(size_t)ge] == 0xFFFF ? (uint32_t)s.nnzPu : (uint32_t)s.sd_pk[(size_t)ge];
+                a.meta[(size_t)(R * a.ept + w) * owners + oid] = (pk * 8u) | (kind << 16) | (1u << 18);
+            }
+    // off-diagonal blocks
+    const int noff = std::max(0, T - 1) * s.bs * s.ow;
+    const bool has_off = !s.so_ptr.empty() && s.so_ptr.size() > (size_t)noff;
+    a.opt = std::max(1, (noff + owners - 1) / owners);
+    for (int e = 0; e < noff && has_off; ++e) a.maxco = std::max(a.maxco, (int)(s.so_ptr[(size_t)e + 1] - s.so_ptr[(size_t)e]));
+    a.maxco = std::max(a.maxco, 1);
+    a.ocon.assign((size_t)a.opt * a.maxco * owners, padw);
+    a.ometa.assign((size_t)a.opt * owners, (uint32_t)s.nnzPu * 8u);
+    for (int e = 0; e < noff && has_off; ++e) {
+        const int w = e / owners, oid = e % owners;
+        uint32_t k = 0;
+        for (uint32_t q = s.so_ptr[(size_t)e]; q < s.so_ptr[(size_t)e + 1]; ++q, ++k) {
+            const Contrib &c = s.so_con[q];
+            a.ocon[((size_t)w * a.maxco + k) * owners + oid] = word(c.row, c.k1, c.k2);
+        }
+        const uint32_t pk = s.so_pk[(size_t)e] == 0xFFFF ? (uint32_t)s.nnzPu : (uint32_t)s.so_pk[(size_t)e];
+        a.ometa[(size_t)w * owners + oid] = (pk * 8u) | (1u << 18);
+    }
 }
 
 } // namespace gomp

@@ -41,6 +41,7 @@ class Info(C.Structure):
         ("batch", C.c_int64), ("n", C.c_int64), ("m", C.c_int64), ("m_used", C.c_int64), ("nnzA", C.c_int64), ("nnzP", C.c_int64),
         ("block_size", C.c_int32), ("num_blocks", C.c_int32), ("offdiag_width", C.c_int32),
         ("linsys", C.c_int32), ("threads_per_cta", C.c_int32), ("ctas_per_sm", C.c_int32), ("num_sms", C.c_int32), ("grid", C.c_int32),
+        ("qps_per_sm", C.c_int32), ("reserved0", C.c_int32),
         ("smem_bytes", C.c_int64), ("workspace_bytes", C.c_int64), ("kernel_launches", C.c_int64),
         ("last_solve_ms", C.c_double), ("last_h2d_ms", C.c_double),
         ("flops_per_iter", C.c_int64), ("smem_bytes_per_iter", C.c_int64),
@@ -52,7 +53,8 @@ class Info(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libgomp_cuda.so")
+    # GOMP_CUDA_LIB: an alternative build of the same library (A/B measurements of kernel variants)
+    return os.environ.get("GOMP_CUDA_LIB") or os.path.join(_HERE, "libgomp_cuda.so")
 
 
 def lib():
