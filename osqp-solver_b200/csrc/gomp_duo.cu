@@ -895,10 +895,12 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                 if (do_info && hasq) B.dxg[(size_t)b * np + (p8 >> 3)] = xn - x[c];
                 x[c] = xn;
             }
+            long long t_sub = kTimers ? clock64() : 0;
             double ztv[RPT];
 #pragma unroll
             for (int j = 0; j < RPT; ++j) ztv[j] = 0.0;
             DUO_DOT(true, RPT, ztv, aA, aR, aRowMine, rpad);
+            if (kTimers && B.prof != nullptr && oid == 0) { const long long n_ = clock64(); atomicAdd(&B.prof[13], (unsigned long long)(n_ - t_sub)); t_sub = n_; }
             // two rows at a time: bounds and rho of both first (independent loads), then the two dependent chains side by side
 #pragma unroll
             for (int j0 = 0; j0 < RPT; j0 += 2) {
@@ -930,7 +932,9 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                     }
                 }
             }
+            if (kTimers && B.prof != nullptr && oid == 0) { const long long n_ = clock64(); atomicAdd(&B.prof[14], (unsigned long long)(n_ - t_sub)); t_sub = n_; }
             OWNERS_SYNC(); // sRHS is overwritten by the next gather, which reads sW
+            if (kTimers && B.prof != nullptr && oid == 0) { const long long n_ = clock64(); atomicAdd(&B.prof[15], (unsigned long long)(n_ - t_sub)); t_sub = n_; }
             DUO_MARK(PH_UPDATE);
 
             if (do_info) {
