@@ -565,7 +565,7 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
     int pos8[CPT]; // 8 * position owned in column slot c, -1: none
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-        const uint16_t p = X.col_pos[c * kDuoOwners + oid];
+        const uint16_t p = c < X.cpt ? X.col_pos[c * kDuoOwners + oid] : (uint16_t)0xFFFFu; // (the table holds X.cpt <= CPT slots)
         pos8[c] = p == 0xFFFFu ? -1 : 8 * (int)p;
     }
     // zero elements behind the arrays (targets of surplus ELL entries)

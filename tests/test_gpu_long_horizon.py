@@ -168,26 +168,50 @@ def test_streamed_general_qp_with_linear_term():
         assert np.abs(got["y"][b] - r.y).max() < REL_TOL * max(1.0, np.abs(r.y).max())
 
 
-def test_prefer_throughput_selects_two_ctas_per_sm():
-    """AUTO + prefer_throughput on the headline shape with a batch of >= 2 QPs per SM: the streamed kernel's
-    small-QP mode (256 threads, two CTAs per SM); same answers as the resident kernel.  Small batches stay resident."""
+def test_prefer_throughput_selects_two_ctas_per_sm(monkeypatch):
+    """Back-end selection on the headline shape.  AUTO takes the two-slot TMEM kernel (two QPs per SM, gomp_duo.cu) whatever
+    the batch size; with that back end disabled (GOMP_NO_DUO), AUTO + prefer_throughput and a batch of >= 2 QPs per SM take
+    the streamed kernel's small-QP mode (256 threads, two CTAs per SM) and small batches stay on the resident kernel.
+    Each of them is compared with the CPU oracle."""
     pkg, O = package(), oracle()
     pat = pkg.problem.Pattern(pkg.problem.default_config())
     B = 640
     d = pkg.problem.generate(pat, 2000, B)
+    ref = oracle_batch(O, pat, d)
+    duo = make_solver(pkg, pat, d)
+    info = duo.info()
+    assert info["linsys"] == 4 and info["threads_per_cta"] == 512 and info["qps_per_sm"] == 2
+    duo.set_warm_start(d["x0"])
+    compare(duo.solve(want_y=True), ref)
+    duo.close()
+    monkeypatch.setenv("GOMP_NO_DUO", "1")
     fast = make_solver(pkg, pat, d, settings=pkg.solver.default_settings(prefer_throughput=1))
     info = fast.info()
     assert info["linsys"] == GLOBAL and info["threads_per_cta"] == 256 and info["ctas_per_sm"] == 2
     fast.set_warm_start(d["x0"])
-    got = fast.solve(want_y=True)
+    compare(fast.solve(want_y=True), ref)
     fast.close()
-    res = make_solver(pkg, pat, d)
-    assert res.info()["linsys"] == 1
-    res.set_warm_start(d["x0"])
-    ref = res.solve(want_y=True)
-    res.close()
-    compare(got, ref)
     few = {k: v[:16] for k, v in d.items()}
     s = make_solver(pkg, pat, few, settings=pkg.solver.default_settings(prefer_throughput=1))
     assert s.info()["linsys"] == 1          # a handful of QPs: latency matters, resident kernel
     s.close()
+    monkeypatch.delenv("GOMP_NO_DUO")
+    s = make_solver(pkg, pat, few)
+    assert s.info()["linsys"] == 4
+    s.close()
+
+
+@pytest.mark.parametrize("kw", [dict(waypoints=4), dict(waypoints=8), dict(waypoints=16), dict(waypoints=24), dict(waypoints=40), dict(waypoints=48),
+                                dict(n_dim=6, waypoints=30), dict(n_balls=2, n_obstacles=2, waypoints=36)])
+def test_two_slot_backend_shapes(kw):
+    """The two-slot TMEM kernel forced (linsys = 4) on shapes whose rows / columns per owner thread are below the compiled
+    variant's (fewer column slots than the template holds, a single row slot, block size 12): oracle parity."""
+    pkg, O = package(), oracle()
+    pat = pkg.problem.Pattern(pkg.problem.default_config(**kw))
+    d = pkg.problem.generate(pat, 300, 20)
+    s = make_solver(pkg, pat, d, settings=pkg.solver.default_settings(linsys=4))
+    assert s.info()["linsys"] == 4
+    s.set_warm_start(d["x0"])
+    got = s.solve(want_y=True)
+    s.close()
+    compare(got, oracle_batch(O, pat, d))

@@ -17,7 +17,14 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-6  # north_star: primal/dual within 1e-6 relative
 
 
+_BACKEND = [0]  # linear-system back end the `env` tests run on (set by the fixture): 0 = AUTO, 1 = resident kernel
+
+
 def make_solver(pkg, pat, d, settings=None, **kw):
+    if settings is None:
+        settings = pkg.solver.default_settings()
+    if settings.linsys == 0:
+        settings.linsys = _BACKEND[0]
     return pkg.solver.BatchQPSolver(pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx,
                                     d["A_val"], d["l"], d["u"], settings=settings, var_order=pat.var_order,
                                     block_size=pat.block_size, **kw)
@@ -38,12 +45,16 @@ def compare(got, ref, want_y=True):
             assert (np.abs(got["y"][ok] - ref["y"][ok]) / ys).max() < REL_TOL
 
 
-@pytest.fixture(scope="module")
-def env():
+@pytest.fixture(scope="module", params=[0, 1], ids=["auto-two-slot", "resident"])
+def env(request):
+    """Every test on the headline shape runs twice: on the back end AUTO picks for it (the two-slot TMEM kernel,
+    gomp_duo.cu -- what bench.py measures) and on the register-resident kernel (gomp_kernel.cuh)."""
     pkg, O = package(), oracle()
     cfg = pkg.problem.default_config()
     pat = pkg.problem.Pattern(cfg)
-    return pkg, O, pat
+    _BACKEND[0] = request.param
+    yield pkg, O, pat
+    _BACKEND[0] = 0
 
 
 def oracle_batch(O, pat, d, settings=None):
@@ -63,6 +74,7 @@ def test_gomp_batch_default_settings(env):
     assert (ref["exit_code"] != 0).any() and (ref["iters"] > 25).any() and (ref["rho_updates"] > 0).any()  # paths exercised
     info = s.info()
     assert info["m_used"] == 1558 and info["block_size"] == 14 and info["num_blocks"] == 50
+    assert info["linsys"] == (4 if _BACKEND[0] == 0 else 1)   # AUTO = two QPs per SM with the factor in tensor memory
     s.close()
 
 
