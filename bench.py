@@ -13,13 +13,18 @@ reference does per QP at src/gomp-solver.h:61-71 (QPSolver ctor + setWarmStart +
   roofline achieved vs measured shared-memory bandwidth (the bound SURVEY.md 8d names for this
            kernel: min(FP64 pipe, shared memory)); FP64 and HBM fractions alongside
   cpu_baseline  the oracle (CPU restatement of OSQP, kind "port") timed on the box's host cores on
-           a bounded sample of the same workload
+           a bounded sample of the same workload, fed as ONE continuous work queue (no thread idles
+           at a pass boundary), the same problem ids as the GPU arm
+  extra    configs[2] (warm SQP x10 on the device), configs[3] (H = 400, batch 1 and 148) and
+           configs[4] (1 048 576 problems sharded over the ranks, assembled on the device from start /
+           goal: strong scaling), each bounded to a few seconds and checked against the oracle
 
 --impl reference times that CPU oracle on all host threads instead (the real reference cannot be
 built offline: it needs osqp-cpp/OSQP/Eigen via CMake FetchContent).
 
 Workload: BASELINE.json configs[1] -- 4096 synthetic 7-DoF GOMP QPs, horizon H=50, per GPU
-(weak scaling across ranks; problems are independent, NCCL only gathers the results).
+(weak scaling across ranks; problems are independent, NCCL gathers every step's results on rank 0
+inside the timed region).
 """
 import argparse
 import json
@@ -107,40 +112,311 @@ def workload(pkg):
     return cfg, pat, desc
 
 
-def time_oracle(pkg, O, pat, count, first_id, nthreads):
-    d = pkg.problem.generate(pat, first_id, count)
+def host_cores():
+    """(logical CPUs usable by this process, physical cores behind them)."""
+    logical = len(os.sched_getaffinity(0))
+    phys = None
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+    except Exception:
+        pass
+    return logical, phys
+
+
+def time_oracle(pkg, O, pat, count, first_id, nthreads, passes=1, data=None):
+    """`passes` passes over problems first_id .. first_id + count - 1 as one continuous work queue (oracle/osqp_ref.c
+    oref_solve_batch_passes): every work item is a full cold setup + warm start + solve of one QP."""
+    d = data if data is not None else pkg.problem.generate(pat, first_id, count)
     t0 = time.perf_counter()
-    r = O.solve_batch(pat.n, pat.m, pat.P_scipy(), (pat.A_colptr, pat.A_rowidx), d["A_val"], d["l"], d["u"], d["x0"], nthreads=nthreads)
+    r = O.solve_batch(pat.n, pat.m, pat.P_scipy(), (pat.A_colptr, pat.A_rowidx), d["A_val"], d["l"], d["u"], d["x0"], nthreads=nthreads,
+                      passes=passes)
     dt = time.perf_counter() - t0
-    return count / dt, dt, r
+    return count * passes / dt, dt, r
+
+
+CPU_NOTE = ("one QP per thread from one continuous work queue over all passes (dynamic, no pass boundary), KKT ordering computed once per "
+            "call (favours the CPU); oracle = CPU restatement of OSQP 0.6, not genuine OSQP/qdldl")
 
 
 def run_reference(args):
-    """CPU arm: the oracle on all host threads, bounded sample of the same workload per step."""
+    """CPU arm: the oracle on all host threads.  A step is one pass over the GPU arm's 4096 problems (ids 0..4095); all timed
+    steps are ONE call, i.e. one continuous queue of steps x 4096 work items, so no thread idles while a long QP of the
+    previous step finishes -- the CPU counterpart of the GPU arm's batches in flight."""
     rank, local_rank, world = rank_env()
     if rank != 0:
         return
     pkg = entry.load_package()
     O = entry.load_oracle()
     cfg, pat, desc = workload(pkg)
-    cores = O.max_threads()
-    sample = 1024
-    times = []
-    for s in range(args.warmup + args.steps):
-        qps, dt, _ = time_oracle(pkg, O, pat, sample, 0, cores)
-        if s >= args.warmup:
-            times.append(dt)
-    total = sum(times)
-    value = sample * len(times) / total
+    logical, phys = host_cores()
+    cores = min(O.max_threads(), logical)
+    sample = BATCH_PER_GPU
+    d = pkg.problem.generate(pat, 0, sample)
+    # bounded: at ~0.3 ms of CPU time per QP and core a pass is 4096 / (cores * 3k) s; cap the passes so the run ends in minutes
+    warm = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, 24))
+    time_oracle(pkg, O, pat, sample, 0, cores, passes=warm, data=d)
+    value, total, _ = time_oracle(pkg, O, pat, sample, 0, cores, passes=steps, data=d)
     line = {"impl": "reference", "metric": "GOMP QPs solved/sec", "value": value, "unit": "QP/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": desc,
-            "cpu_baseline": {"value": value, "unit": "QP/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} QPs of the workload per step (problem ids 0..{sample - 1}), one QP per thread, KKT ordering computed once "
-                                       "per batch (favours the CPU); oracle = restatement of OSQP 0.6, not genuine OSQP/qdldl"},
+            "cpu_baseline": {"value": value, "unit": "QP/s", "cores": cores, "logical_cpus": logical, "physical_cores": phys, "kind": "port",
+                             "sample": f"{steps} timed passes (after {warm} untimed) over the GPU arm's {sample} QPs (problem ids 0..{sample - 1}), "
+                                       f"{total:.2f} s wall; " + CPU_NOTE},
             "e2e": {"value": value, "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def bind_near_gpu(index):
+    """Multi-rank runs: keep this rank's threads (and therefore the pages of its pinned host buffers) on the NUMA node of its
+    GPU -- eight ranks streaming 328 MB per step each out of one node's memory was the e2e limiter of round 1."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                             text=True, timeout=20).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        cpus = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
+def strong_scaling(pkg, pat, rank, world, local_rank, torch, dist):
+    """BASELINE.json configs[4]: TOTAL problems of configs[1] sharded over the ranks (contiguous id ranges), strong scaling.
+    Per chunk the host hands over start / goal only (16 N bytes per QP); A_val, l, u and the warm start are assembled on
+    the device (gomp_device_assemble), solved, and x / exit code / iterations return to pinned host memory.  One pass."""
+    P, S = pkg.problem, pkg.solver
+    total = int(os.environ.get("GOMP_BENCH_STRONG_PROBLEMS", str(1 << 20)))
+    if total <= 0:
+        return None
+    chunk = int(os.environ.get("GOMP_BENCH_STRONG_CHUNK", "16384"))
+    nh = 4
+    per = (total + world - 1) // world
+    lo, hi = rank * per, min(total, (rank + 1) * per)
+    count = max(0, hi - lo)
+    chunk = max(1, min(chunk, count))
+    nchunks = (count + chunk - 1) // chunk
+    N = pat.cfg.n_dim
+    t_gen = time.perf_counter()
+    sg_host = torch.empty((max(count, 1), 2 * N), dtype=torch.float64).pin_memory()
+    if count:
+        P.start_goal(pat, lo, count, out=sg_host.numpy()[:count])
+    t_gen = time.perf_counter() - t_gen
+    streams = [torch.cuda.Stream() for _ in range(nh)]
+    solvers, scenes, bufs, outs = [], [], [], []
+    tmpl = P.generate(pat, 0, 1)
+    for k in range(nh):
+        st = S.default_settings(borrow_inputs=1, stream=streams[k].cuda_stream, device=local_rank)
+        solvers.append(S.BatchQPSolver(pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx, batch=chunk,
+                                       settings=st, var_order=pat.var_order, block_size=pat.block_size))
+        sc = P.DeviceScene(pat, None, chunk, device=local_rank)
+        sc.set_template(tmpl)
+        scenes.append(sc)
+        bufs.append({k_: torch.empty(shape, dtype=torch.float64, device="cuda") for k_, shape in
+                     dict(A_val=(chunk, pat.nnzA), l=(chunk, pat.m), u=(chunk, pat.m), x0=(chunk, pat.n), sg=(chunk, 2 * N)).items()})
+        outs.append(dict(x=torch.empty((chunk, pat.n), dtype=torch.float64).pin_memory(),
+                         ints=torch.empty((2, chunk), dtype=torch.int32).pin_memory()))
+    hist = np.zeros(11, dtype=np.int64)
+    iters_sum = 0
+
+    def submit(c):
+        k = c % nh
+        a, b = c * chunk, min(count, (c + 1) * chunk)
+        if b - a < chunk:   # ragged last chunk: pad with the chunk's first problem (results of the padding are dropped)
+            sg_host_chunk = torch.cat([sg_host[a:b], sg_host[a:a + 1].expand(chunk - (b - a), 2 * N)]).pin_memory()
+        else:
+            sg_host_chunk = sg_host[a:b]
+        with torch.cuda.stream(streams[k]):
+            bufs[k]["sg"].copy_(sg_host_chunk, non_blocking=True)
+        bufs[k]["keep"] = sg_host_chunk
+        scenes[k].assemble(bufs[k]["sg"], bufs[k]["A_val"], bufs[k]["l"], bufs[k]["u"], bufs[k]["x0"], stream=streams[k].cuda_stream)
+        solvers[k].setup(bufs[k]["A_val"], bufs[k]["l"], bufs[k]["u"])
+        solvers[k].set_warm_start(bufs[k]["x0"])
+        solvers[k].solve_async()
+        solvers[k].get_async(x=outs[k]["x"], exit_code=outs[k]["ints"][0], iters=outs[k]["ints"][1])
+
+    def collect(c):
+        nonlocal iters_sum
+        k = c % nh
+        solvers[k].sync()
+        valid = min(count, (c + 1) * chunk) - c * chunk
+        ints = outs[k]["ints"].numpy()
+        hist[:] += np.bincount(ints[0][:valid], minlength=11)[:11]
+        iters_sum += int(ints[1][:valid].sum())
+
+    # untimed: one small chunk through every handle (kernel load, workspace sizing)
+    if nchunks:
+        for c in range(min(nh, nchunks)):
+            submit(c)
+        for c in range(min(nh, nchunks)):
+            collect(c)
+    hist[:] = 0
+    iters_sum = 0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main = torch.cuda.current_stream()
+    ev0.record(main)
+    for s_ in streams:
+        s_.wait_event(ev0)
+    t0 = time.perf_counter()
+    for c in range(nchunks):
+        if c >= nh:
+            collect(c - nh)
+        submit(c)
+    for c in range(max(0, nchunks - nh), nchunks):
+        collect(c)
+    for s_ in streams:
+        e = torch.cuda.Event()
+        e.record(s_)
+        main.wait_event(e)
+    ev1.record(main)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    for sv in solvers:
+        sv.close()
+    for sc in scenes:
+        sc.close()
+    stats = torch.tensor([dev_ms, wall * 1e3, t_gen * 1e3, float(iters_sum)] + hist.astype(np.float64).tolist(), dtype=torch.float64, device="cuda")
+    allr = [stats]
+    if world > 1:
+        dist.barrier()
+        allr = [torch.empty_like(stats) for _ in range(world)]
+        dist.all_gather(allr, stats)
+    if rank != 0:
+        return None
+    rows = np.stack([t.cpu().numpy() for t in allr])
+    dev_max, wall_max = float(rows[:, 0].max()), float(rows[:, 1].max())
+    return {"workload": f"BASELINE.json configs[4]: {total} problems of configs[1] sharded over {world} GPU(s), contiguous id ranges, "
+                        f"chunks of {chunk} through {nh} handles per GPU; A_val / l / u / x0 assembled on the device from start / goal",
+            "problems": total, "n_gpus": world, "scaling": "strong",
+            "device_ms_max_over_ranks": dev_max, "wall_ms_max_over_ranks": wall_max,
+            "qps_device_timed": total / (dev_max * 1e-3), "qps_wall": total / (wall_max * 1e-3),
+            "rank_device_ms": [round(float(v), 1) for v in rows[:, 0]],
+            "h2d_bytes_per_qp": 16 * N, "d2h_bytes_per_qp": 8 * pat.n + 8,
+            "host_start_goal_generation_ms_untimed": float(rows[:, 2].max()),
+            "exit_code_hist": rows[:, 4:].sum(axis=0).astype(np.int64).tolist(), "iters_mean": float(rows[:, 3].sum() / total)}
+
+
+def extra_sqp_sequence(pkg, O, torch, batch=4096, rounds=10, cpu_sample=64):
+    """BASELINE.json configs[2]: `batch` QPs x `rounds` warm-started SQP rounds (withObstacles(x) -> update -> solve, reference
+    src/gomp-solver.h:70-88 without the early exit) with the data plane on the device; the oracle runs a sample of it."""
+    import concurrent.futures as cf
+    P, S = pkg.problem, pkg.solver
+    pat = P.Pattern(P.default_config())
+    d = P.generate(pat, 0, batch)
+
+    def device_path():
+        stream = torch.cuda.Stream()
+        dev = {k: torch.from_numpy(d[k]).cuda() for k in ("A_val", "l", "u", "x0")}
+        st = S.default_settings(borrow_inputs=1, stream=stream.cuda_stream)
+        s = S.BatchQPSolver(pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx, dev["A_val"], dev["l"], dev["u"],
+                            batch=batch, settings=st, var_order=pat.var_order, block_size=pat.block_size)
+        sc = P.DeviceScene(pat, 0, batch)
+        x = torch.empty((batch, pat.n), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        s.set_warm_start(dev["x0"])
+        hist = []
+        for r in range(rounds):
+            s.solve_async()
+            got = s.get(x=x)
+            hist.append((got["exit_code"].copy(), got["iters"].copy()))
+            if r + 1 < rounds:
+                sc.relinearize(x, dev["A_val"], dev["l"], dev["u"], x_fallback=dev["x0"], stream=stream.cuda_stream)
+                s.update(dev["A_val"], dev["l"], dev["u"])
+        stream.synchronize()
+        dt = time.perf_counter() - t0
+        linsys = s.info()["linsys"]
+        s.close()
+        sc.close()
+        return dt, hist, linsys
+
+    device_path()
+    t_dev, hist, linsys = device_path()
+    Ps = pat.P_scipy()
+    nthreads = min(O.max_threads(), len(os.sched_getaffinity(0)))
+
+    def one(b):
+        ref = O.Solver(Ps, pat.A_scipy(d["A_val"][b]), d["l"][b], d["u"][b])
+        ref.warm_start_x(d["x0"][b])
+        out = []
+        for r in range(rounds):
+            ref.solve()
+            out.append((ref.exit_code, ref.iter))
+            if r + 1 < rounds:
+                xs = np.where(np.isnan(ref.x), d["x0"][b], ref.x)
+                upd = P.relinearize(pat, b, xs[None, :], nthreads=1)
+                ref.update(upd["A_val"][0], upd["l"][0], upd["u"][0])
+        return out
+    n_cpu = min(cpu_sample, batch)
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(nthreads) as ex:
+        cpu = list(ex.map(one, range(n_cpu)))
+    t_cpu = time.perf_counter() - t0
+    # the host facade re-linearises for the oracle, the device kernel for the GPU (they differ through sin / cos rounding), so the
+    # first round is the bit-comparable one; later rounds are reported as the share of (problem, round) pairs that agree
+    code_eq = np.mean([[hist[r][0][b] == cpu[b][r][0] for r in range(rounds)] for b in range(n_cpu)])
+    iter_eq = np.mean([[hist[r][1][b] == cpu[b][r][1] for r in range(rounds)] for b in range(n_cpu)])
+    gpu_rate, cpu_rate = batch * rounds / t_dev, n_cpu * rounds / t_cpu
+    return {"workload": f"BASELINE.json configs[2]: {batch} QPs x {rounds} warm-started SQP rounds (N=7, H=50), data plane on the device",
+            "qp_solves_per_s": gpu_rate, "seconds": t_dev, "linsys": linsys,
+            "cpu_oracle": {"sample": n_cpu, "threads": nthreads, "qp_solves_per_s": cpu_rate, "seconds": t_cpu}, "vs_cpu": gpu_rate / cpu_rate,
+            "round0_status_equal": bool(all(hist[0][0][b] == cpu[b][0][0] for b in range(n_cpu))),
+            "round0_iterations_equal": bool(all(hist[0][1][b] == cpu[b][0][1] for b in range(n_cpu))),
+            "all_rounds_status_agreement": float(code_eq), "all_rounds_iterations_agreement": float(iter_eq)}
+
+
+def extra_long_horizon(pkg, O, W=400, batches=(1, 148), cpu_sample=16):
+    """BASELINE.json configs[3]: N=7, H=400 on the streamed back end, batch 1 and one QP per SM, beside the oracle."""
+    P, S = pkg.problem, pkg.solver
+    pat = P.Pattern(P.default_config(waypoints=W))
+    nmax = max(batches)
+    d = P.generate(pat, 0, nmax)
+    out = {"workload": f"BASELINE.json configs[3]: N=7, H={W} (n={pat.n}, m={pat.m}, nnzA={pat.nnzA})"}
+    results = None
+    for batch in batches:
+        sub = {k: d[k][:batch] for k in ("A_val", "l", "u", "x0")}
+        s = S.BatchQPSolver(pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx, sub["A_val"], sub["l"], sub["u"],
+                            var_order=pat.var_order, block_size=pat.block_size)
+        best = 1e30
+        for _ in range(3):
+            s.setup(sub["A_val"], sub["l"], sub["u"])
+            s.set_warm_start(sub["x0"])
+            results = s.solve()
+            best = min(best, s.info()["last_solve_ms"])
+        out[f"ms_b{batch}"] = best
+        out[f"qps_b{batch}"] = batch / best * 1e3
+        out["linsys"] = s.info()["linsys"]
+        s.close()
+    n_cpu = min(cpu_sample, nmax)
+    nthreads = min(n_cpu, O.max_threads(), len(os.sched_getaffinity(0)))
+    t0 = time.perf_counter()
+    ref = O.solve_batch(pat.n, pat.m, pat.P_scipy(), (pat.A_colptr, pat.A_rowidx), d["A_val"][:n_cpu], d["l"][:n_cpu], d["u"][:n_cpu], d["x0"][:n_cpu],
+                        nthreads=nthreads)
+    t_cpu = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    O.solve_batch(pat.n, pat.m, pat.P_scipy(), (pat.A_colptr, pat.A_rowidx), d["A_val"][:1], d["l"][:1], d["u"][:1], d["x0"][:1], nthreads=1)
+    t_cpu1 = time.perf_counter() - t1
+    out["cpu_oracle"] = {"sample": n_cpu, "threads": nthreads, "qps": n_cpu / t_cpu, "ms_b1": t_cpu1 * 1e3}
+    out["vs_cpu_b1"] = t_cpu1 * 1e3 / out[f"ms_b{batches[0]}"]
+    out[f"vs_cpu_b{nmax}"] = out[f"qps_b{nmax}"] / (n_cpu / t_cpu)
+    out["status_equal"] = bool((results["exit_code"][:n_cpu] == ref["exit_code"]).all())
+    out["iterations_equal"] = bool((results["iters"][:n_cpu] == ref["iters"]).all())
+    return out
 
 
 def run_gpu(args):
@@ -169,6 +445,8 @@ def run_gpu(args):
     cfg, pat, desc = workload(pkg)
     B = BATCH_PER_GPU
     first_id = rank * B
+    full_affinity = os.sched_getaffinity(0)
+    numa_cpus = bind_near_gpu(local_rank) if world > 1 else None
 
     # ---- synthetic inputs: generated on the host into pinned memory, then made resident in HBM
     host = {k: torch.empty(shape, dtype=torch.float64).pin_memory() for k, shape in
@@ -207,13 +485,20 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    gathered = [torch.empty_like(x_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # N > 1: the problems are independent, the only collective is the gather of every step's results {x, exit code,
+    # iterations} on rank 0 (NCCL over NVLink), queued behind the step's solve on the step's stream
+    if world > 1:
+        xg = [torch.empty((B, pat.n), dtype=torch.float64, device="cuda") for _ in range(PIPE)]
+        ig = [torch.empty((2, B), dtype=torch.int32, device="cuda") for _ in range(PIPE)]
+        xg_all = [[torch.empty_like(xg[0]) for _ in range(world)] for _ in range(PIPE)] if rank == 0 else None
+        ig_all = [[torch.empty_like(ig[0]) for _ in range(world)] for _ in range(PIPE)] if rank == 0 else None
 
-    def gather_results():
-        # problems are independent: the only collective is the final gather of the solutions (NCCL)
-        if world > 1:
-            solvers[-1].get(x=x_dev, exit_code=code, iters=iters, rho_updates=rup)
-            dist.gather(x_dev, gathered, dst=0)
+    def gather_step(k):
+        j = k % PIPE
+        solvers[j].get_async(x=xg[j], exit_code=ig[j][0], iters=ig[j][1])
+        with torch.cuda.stream(streams[j]):
+            dist.gather(xg[j], xg_all[j] if rank == 0 else None, dst=0)
+            dist.gather(ig[j], ig_all[j] if rank == 0 else None, dst=0)
 
     def run_steps(nsteps):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -222,6 +507,8 @@ def run_gpu(args):
             st_.wait_event(ev0)
         for k in range(nsteps):
             step_resident(k)
+            if world > 1:
+                gather_step(k)
         for st_ in streams:
             e = torch.cuda.Event()
             e.record(st_)
@@ -229,23 +516,26 @@ def run_gpu(args):
         ev1.record(main)
         return ev0, ev1
 
-    run_steps(args.warmup)
-    barrier()
-    gather_results()
+    run_steps(max(args.warmup, PIPE))  # every handle has run once before the timed region (first use sizes its workspace)
     barrier()
     launches0 = sum(sv.info()["kernel_launches"] for sv in solvers)
     sampler = ClockSampler(local_rank)
     sampler.start()
     kernel_ms = []
     barrier()
-    ev0, ev1 = run_steps(args.steps)
-    gather_results()  # N > 1: the NCCL gather of the last batch's solutions, inside the timed region
-    if world > 1:
-        ev1 = torch.cuda.Event(enable_timing=True)
-        ev1.record(main)
+    ev0, ev1 = run_steps(args.steps)  # N > 1: includes the NCCL gather of every step's results
     barrier()
     clocks = sampler.stop()
     total_ms = ev0.elapsed_time(ev1)
+    gathered_ok = None
+    if world > 1 and rank == 0:
+        # the last step's gathered block of every rank against this rank's own results (all ranks solve their own ids; rank 0's
+        # block must be its own x bit for bit, the others must carry valid exit codes)
+        j = (args.steps - 1) % PIPE
+        own = torch.empty_like(xg[j])
+        solvers[j].get(x=own)
+        codes = torch.stack([t[0] for t in ig_all[j]]).cpu().numpy()
+        gathered_ok = bool(torch.equal(torch.nan_to_num(own), torch.nan_to_num(xg_all[j][0]))) and bool(((codes >= 0) & (codes <= 10)).all())
     r = solver.get(x=x_dev, exit_code=code, iters=iters, rho_updates=rup)
     info = solver.info()
     launches = sum(sv.info()["kernel_launches"] for sv in solvers) - launches0
@@ -309,12 +599,21 @@ def run_gpu(args):
     h2d = 8 * B * (pat.nnzA + 2 * pat.m + pat.n)
     d2h = B * (8 * pat.n + 12)
 
+    for sv in e2e_solvers:
+        sv.close()
+    del e2e_solvers, x_hosts, dev
+    torch.cuda.empty_cache()
+    strong = None
+    if os.environ.get("GOMP_BENCH_EXTRA", "1") != "0":
+        strong = strong_scaling(pkg, pat, rank, world, local_rank, torch, dist)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    os.sched_setaffinity(0, full_affinity)
 
-    # ---- roofline of the ADMM kernel (work model: DESIGN.md / gomp_batch_info)
+    # ---- roofline of the ADMM kernel (work model: DESIGN.md section 5 / gomp_batch_info)
     it = r["iters"].astype(np.float64)
     nfact = 1.0 + r["rho_updates"].astype(np.float64)
     checks = np.ceil(it / 25.0)
@@ -327,41 +626,36 @@ def run_gpu(args):
     hbm_peak, hbm_src = 6650.0, "fallback"
     if os.path.exists(peaks_path):
         hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    # One launch = one step's 4096 QPs.  Launches of consecutive steps overlap on the GPU (PIPE handles), so the time a launch
+    # costs in steady state is the step time of the timed region -- `frac` is formed with it and is reproducible from this
+    # line's own fields (achieved = algorithmic_smem_bytes / ms_per_step).  `frac_solo` uses the duration of one launch
+    # running alone (CUDA events on its stream), which is dominated by the tail of its max_iter QPs.
+    step_s = total_ms / args.steps * 1e-3
     ksec = kernel_avg_ms * 1e-3
-    # DRAM bytes of one launch from the committed ncu --set full capture (same kernel, same workload)
-    traffic, traffic_src = None, None
-    streamed = int(info["linsys"]) == 2  # AUTO + prefer_throughput: the two-QPs-per-SM mode of the streamed kernel
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic_stream.json" if streamed else "r01_ncu_traffic.json")
+    linsys = int(info["linsys"])
+    kernel_name = {4: "gomp_duo_kernel<9,4,14>", 2: "gomp_admm_stream_kernel<14,256,true>"}.get(linsys, "gomp_admm_kernel<4,2,14>")
+    # DRAM bytes and pipe utilisation of one launch from the committed ncu --set full capture (same kernel, same workload)
+    traffic, traffic_src, ncu = None, None, {}
+    tpath = os.path.join(ROOT, "profiles", {4: "r02_ncu_duo.json", 2: "r01_ncu_traffic_stream.json"}.get(linsys, "r01_ncu_traffic.json"))
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * B / tj["qps_per_launch"]
         traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum per launch, " + tj["capture"]
-    roofline = {"bound": "smem", "achieved": smem_bytes / ksec / 1e9, "peak": smem_peak, "unit": "GB/s",
-                "frac": smem_bytes / ksec / 1e9 / smem_peak, "traffic": traffic, "traffic_source": traffic_src,
+        ncu = {k: tj[k] for k in ("lsu_wavefront_pct", "issue_pct", "warp_instructions_per_qp", "smem_wavefronts_per_qp") if k in tj}
+    roofline = {"bound": "smem", "achieved": smem_bytes / step_s / 1e9, "peak": smem_peak, "unit": "GB/s",
+                "frac": smem_bytes / step_s / 1e9 / smem_peak, "frac_solo": smem_bytes / ksec / 1e9 / smem_peak,
+                "algorithmic_smem_bytes": float(smem_bytes), "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_hbm_bytes": hbm_bytes,
                 "peak_source": "measured live (gomp_measure_peaks: conflict-free 16-byte shared-memory loads on all SMs)",
-                "kernel": "gomp_admm_stream_kernel<14,256,true>" if streamed else "gomp_admm_kernel<4,2,14>", "kernel_ms": kernel_avg_ms,
-                "fp64": {"achieved": flops / ksec / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops / ksec / 1e12 / fp64_peak,
+                "kernel": kernel_name, "kernel_ms": total_ms / args.steps, "kernel_ms_solo": kernel_avg_ms,
+                "fp64": {"achieved": flops / step_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops / step_s / 1e12 / fp64_peak,
                          "peak_source": "measured live (gomp_measure_peaks: 8 independent DFMA chains per thread)"},
-                "hbm": {"achieved": hbm_bytes / ksec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_bytes / ksec / 1e9 / hbm_peak,
+                "hbm": {"achieved": hbm_bytes / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_bytes / step_s / 1e9 / hbm_peak,
                         "peak_source": hbm_src},
                 "note": "SURVEY.md 8d: not an HBM- or tensor-bound kernel; bound = min(FP64 pipe, shared-memory bandwidth), "
                         "real limiter = dependency chain of the block substitutions",
                 "mean_iters": float(it.mean()), "mean_factorizations": float(nfact.mean())}
-
-    # ---- CPU baseline on the host cores (bounded sample)
-    O = entry.load_oracle()
-    cores = O.max_threads()
-    sample, passes = 1024, 3
-    time_oracle(pkg, O, pat, 256, first_id, cores)          # untimed: thread start-up, first-touch of the work arrays
-    cpu_dt = 0.0
-    for _ in range(passes):
-        _, dt, ref = time_oracle(pkg, O, pat, sample, first_id, cores)
-        cpu_dt += dt
-    cpu_all = passes * sample / cpu_dt
-    cpu_1, _, _ = time_oracle(pkg, O, pat, 64, first_id, 1)
-    same_code = bool((ref["exit_code"] == r["exit_code"][:sample]).all())
-    same_iters = bool((ref["iters"] == r["iters"][:sample]).all())
+    roofline.update(ncu)
 
     line = {"metric": "GOMP QPs solved/sec", "value": value, "unit": "QP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -369,17 +663,47 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(launches),
-            "ranks": {"device_ms": [round(v, 3) for v in rank_ms], "sm_mhz": rank_mhz},
+            "ranks": {"device_ms": [round(v, 3) for v in rank_ms], "sm_mhz": rank_mhz, "numa_cpus_rank0": numa_cpus,
+                      "per_step_gather": None if world == 1 else {"collective": "NCCL gather of {x, exit code, iterations} of every step on rank 0, "
+                                                                                "inside the timed region",
+                                                                  "bytes_per_step_into_rank0": (world - 1) * B * (8 * pat.n + 8),
+                                                                  "last_step_block_ok": gathered_ok}},
             "roofline": roofline,
-            "cpu_baseline": {"value": cpu_all, "unit": "QP/s", "cores": cores, "kind": "port", "single_core_value": cpu_1,
-                             "sample": f"{sample} QPs of the same workload (problem ids {first_id}..{first_id + sample - 1}) on all {cores} host threads, "
-                                       f"one QP per thread, {passes} passes after one untimed pass, {cpu_dt:.2f} s wall; oracle = CPU restatement of OSQP 0.6 (not genuine OSQP/qdldl), "
-                                       "KKT ordering shared across the batch",
-                             "status_equal_to_gpu": same_code, "iterations_equal_to_gpu": same_iters},
             "clocks": clocks,
-            "solver": {"ctas_per_sm": info["ctas_per_sm"], "smem_bytes_per_cta": info["smem_bytes"], "threads_per_cta": info["threads_per_cta"],
+            "solver": {"linsys": linsys, "qps_per_sm": info["qps_per_sm"], "ctas_per_sm": info["ctas_per_sm"], "smem_bytes_per_cta": info["smem_bytes"],
+                       "threads_per_cta": info["threads_per_cta"],
                        "grid": info["grid"], "exit_code_hist": np.bincount(r["exit_code"], minlength=11).tolist(),
                        "iters_mean": float(it.mean()), "iters_max": int(it.max())}}
+
+    O = entry.load_oracle()
+    extra = {}
+    if strong is not None:
+        extra["strong_scaling"] = strong
+    if world == 1:
+        # ---- CPU baseline on the host cores (rank 0, N = 1 only): the GPU arm's own 4096 problems, continuous queue
+        logical, phys = host_cores()
+        cores = min(O.max_threads(), logical)
+        d_cpu = {k: host[k].numpy() for k in ("A_val", "l", "u", "x0")}
+        passes = 3
+        time_oracle(pkg, O, pat, 256, first_id, cores, data={k: v[:256] for k, v in d_cpu.items()})  # untimed: thread start-up, first touch
+        cpu_all, cpu_dt, ref = time_oracle(pkg, O, pat, B, first_id, cores, passes=passes, data=d_cpu)
+        cpu_1, _, _ = time_oracle(pkg, O, pat, 96, first_id, 1, data={k: v[:96] for k, v in d_cpu.items()})
+        line["cpu_baseline"] = {"value": cpu_all, "unit": "QP/s", "cores": cores, "logical_cpus": logical, "physical_cores": phys, "kind": "port",
+                                "single_core_value": cpu_1, "all_core_over_single_core": cpu_all / cpu_1,
+                                "sample": f"{passes} passes over the GPU arm's {B} QPs (problem ids {first_id}..{first_id + B - 1}) on all {cores} host threads, "
+                                          f"{cpu_dt:.2f} s wall after one untimed 256-QP call; " + CPU_NOTE,
+                                "status_equal_to_gpu": bool((ref["exit_code"] == r["exit_code"]).all()),
+                                "iterations_equal_to_gpu": bool((ref["iters"] == r["iters"]).all())}
+        if os.environ.get("GOMP_BENCH_EXTRA", "1") != "0":
+            try:
+                extra["sqp_sequence"] = extra_sqp_sequence(pkg, O, torch)
+            except Exception as e:  # an extra must never take the headline line down
+                extra["sqp_sequence"] = {"error": repr(e)}
+            try:
+                extra["long_horizon_h400"] = extra_long_horizon(pkg, O)
+            except Exception as e:
+                extra["long_horizon_h400"] = {"error": repr(e)}
+    line["extra"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

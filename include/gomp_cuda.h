@@ -88,7 +88,8 @@ typedef struct gomp_settings {
     double eps_dual_inf;           /* 1e-4 */
     int32_t scaled_termination;    /* 0 */
     int32_t check_termination;     /* 25 */
-    int32_t warm_start;            /* 1 */
+    int32_t warm_start;            /* 1 (0 is rejected: iterates always persist across solves of a handle, as the reference's
+                                      QPSolver relies on; a cold start is gomp_batch_setup) */
     int32_t verbose;               /* 0 (the reference sets true; output only) */
     /* device side */
     int32_t device;                /* CUDA device ordinal, -1 = current */
@@ -96,7 +97,7 @@ typedef struct gomp_settings {
     int32_t linsys;                /* GOMP_LINSYS_* */
     int32_t block_size;            /* stage-block size of the variable ordering, 0 = detect */
     const int64_t *var_order;      /* n entries: position p holds variable var_order[p]; NULL = detect */
-    int32_t threads_per_cta;       /* 0 = auto */
+    int32_t threads_per_cta;       /* must be 0 (fixed per back end; reported by gomp_batch_info) */
     int32_t borrow_inputs;         /* 1: device-pointer inputs are used in place (caller keeps them alive until the next setup/update) */
     int32_t prefer_throughput;     /* 1 (with linsys = AUTO): when the QP also fits the two-CTAs-per-SM mode of the streamed back end
                                       (block size 14 with the uniform 2-wide off-diagonal pattern, < 113 KB of shared memory per
@@ -167,6 +168,12 @@ int gomp_batch_update(gomp_batch *h, const double *A_val, const double *l, const
 int gomp_batch_get(gomp_batch *h, double *x, double *y, int32_t *exit_code, int32_t *iters,
                    int32_t *rho_updates);
 
+/* The same copies queued on the handle's stream WITHOUT waiting for them: for device destinations (a collective
+ * that follows on another stream orders itself after the handle's stream) or pinned host buffers read after
+ * gomp_batch_sync.  Exit codes are mapped to OsqpExitCode values on the device. */
+int gomp_batch_get_async(gomp_batch *h, double *x, double *y, int32_t *exit_code, int32_t *iters,
+                         int32_t *rho_updates);
+
 /* Extra per-problem diagnostics: pri_res, dua_res, rho, obj_val: [batch] or NULL. */
 int gomp_batch_get_info(gomp_batch *h, double *pri_res, double *dua_res, double *rho,
                         double *obj_val);
@@ -193,6 +200,33 @@ int gomp_device_memcpy(void *dst, const void *src, int64_t bytes, void *stream);
 int gomp_batch_info(gomp_batch *h, gomp_info *info);
 int gomp_batch_sync(gomp_batch *h);
 int gomp_batch_destroy(gomp_batch *h);
+
+/* ---- one batch over several GPUs of one process (the QPs are independent, so the batch shards
+ * with no exchange during the solve; the only data movement between devices is the gather of the results).
+ * Problem b lives on shard b % n_shards ("interleaved": consecutive problems of a GOMP batch are similar, so
+ * every device sees the same mix of short and long solves and none of them holds the tail).  Every entry point
+ * takes and returns whole-batch arrays in the caller's order, host or device pointers (a device pointer may
+ * live on any GPU: the copies go through peer access / NVLink when the devices allow it); inputs are staged
+ * onto their shard's device with strided copies and the shards' results are scattered back the same way.
+ * Calls mirror gomp_batch_*: what QPSolver's members are for one QP (reference src/osqp-wrapper.h:16-54),
+ * these are for a batch spread over `n_devices` GPUs. */
+typedef struct gomp_mg gomp_mg;
+
+/* devices: CUDA ordinals [n_devices] (NULL: 0 .. n_devices-1; n_devices <= 0: every visible device).
+ * settings->device and ->stream are ignored (one stream per shard, owned by the handle). */
+int gomp_mg_create(gomp_mg **out, const gomp_settings *settings, const int32_t *devices, int32_t n_devices,
+                   int64_t batch, int64_t n, int64_t m, const int64_t *P_colptr, const int64_t *P_rowidx,
+                   const double *P_val, const int64_t *A_colptr, const int64_t *A_rowidx);
+int gomp_mg_setup(gomp_mg *g, const double *A_val, const double *l, const double *u, const double *q);
+int gomp_mg_warm_start_x(gomp_mg *g, const double *x0);
+int gomp_mg_update(gomp_mg *g, const double *A_val, const double *l, const double *u, const double *q);
+int gomp_mg_solve(gomp_mg *g); /* launches every shard's solve; asynchronous */
+/* waits for every shard and gathers: x [batch, n], y [batch, m], exit_code / iters / rho_updates [batch] */
+int gomp_mg_get(gomp_mg *g, double *x, double *y, int32_t *exit_code, int32_t *iters, int32_t *rho_updates);
+/* shard k: its gomp_batch handle (for gomp_batch_info etc.), device ordinal and number of problems */
+int gomp_mg_shard(gomp_mg *g, int32_t k, gomp_batch **handle, int32_t *device, int64_t *count);
+int gomp_mg_num_shards(gomp_mg *g);
+int gomp_mg_destroy(gomp_mg *g);
 
 /* Measured roofline denominators of the current device for this kernel class: FP64 FMA throughput
  * (TFLOP/s) and aggregate shared-memory load bandwidth (GB/s).  Either pointer may be NULL. */

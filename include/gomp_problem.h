@@ -82,6 +82,16 @@ typedef struct gomp_device_scene gomp_device_scene;
 int gomp_device_scene_create(gomp_device_scene **out, const gomp_problem_config *cfg, int64_t count, int64_t n, int64_t m,
                              int64_t nnzA, const double *lines /* host, gomp_problem_scene */, int64_t n_rows,
                              const int32_t *rows, const int32_t *kidx /* host, gomp_problem_cart_rows */, int32_t device);
+/* gomp_problem_generate on the device (BASELINE.json configs[4]: inputs built on the GPU so that only start / goal cross
+ * PCIe, 16 N bytes per QP instead of 8 (nnzA + 2 m + n)).  set_template: (A_val, l, u) of ANY one problem of the
+ * configuration (host or device arrays of one problem) -- every row that does not depend on the problem is taken from it.
+ * assemble: start_goal [count, 2N] (device) -> the scene's obstacle lines (`lines` may be NULL at scene creation), the
+ * straight-line warm start x0 [count, n], and A_val / l / u [count, .] exactly as reference src/gomp-solver.h:57-64 +
+ * :105-116 build them: start pinned at waypoint 0, goal at waypoint W-3, Cartesian rows linearised around x0.  All device
+ * arrays, asynchronous on `stream`. */
+int gomp_device_scene_set_template(gomp_device_scene *s, const double *A_val, const double *l, const double *u);
+int gomp_device_assemble(gomp_device_scene *s, const double *start_goal, double *A_val, double *l, double *u, double *x0,
+                         void *stream);
 /* x [count, n] (device): trajectories to linearise around; a problem whose x is NaN (infeasible QP) uses its
  * row of x_fallback (nullable: then that problem is left untouched).  A_val [count, nnzA], l/u [count, m]
  * (device) are updated in place; only the Cartesian rows are written.  Asynchronous on `stream`. */

@@ -1060,7 +1060,7 @@ int oref_max_threads(void) {
 }
 
 typedef struct {
-    I batch, n, m, nnzA;
+    I batch, n, m, nnzA, total; /* total = passes * batch work items, item w solves QP w % batch */
     const I *Pp, *Pi, *Ap, *Ai, *perm;
     const double *Px, *Ax, *l, *u, *x0;
     const oref_settings *settings;
@@ -1074,7 +1074,8 @@ static void *batch_worker(void *arg) {
     batch_job *J = (batch_job *)arg;
     for (;;) {
         I b = (I)__sync_fetch_and_add(&J->next, 1);
-        if (b >= J->batch) break;
+        if (b >= J->total) break;
+        b %= J->batch;
         oref_solver *s = oref_setup(J->n, J->m, J->Pp, J->Pi, J->Px, NULL, J->Ap, J->Ai,
                                     J->Ax + b * J->nnzA, J->l + b * J->m, J->u + b * J->m,
                                     J->settings, J->perm);
@@ -1094,20 +1095,23 @@ static void *batch_worker(void *arg) {
     return NULL;
 }
 
-int oref_solve_batch(I batch, I n, I m, const I *Pp, const I *Pi, const double *Px, const I *Ap,
-                     const I *Ai, const double *Ax, const double *l, const double *u,
-                     const double *x0, const oref_settings *settings, int nthreads, double *x,
-                     double *y, int *exit_code, int *iters, int *rho_updates) {
+/* `passes` passes over the batch as ONE continuous work queue (bench.py's CPU arm: no thread idles at a pass boundary
+ * while a long QP of the previous pass finishes; every pass is a full cold setup + warm start + solve of each QP). */
+int oref_solve_batch_passes(I batch, I n, I m, const I *Pp, const I *Pi, const double *Px, const I *Ap,
+                            const I *Ai, const double *Ax, const double *l, const double *u,
+                            const double *x0, const oref_settings *settings, int nthreads, int passes, double *x,
+                            double *y, int *exit_code, int *iters, int *rho_updates) {
     I *perm = (I *)xcalloc((size_t)(n + m), sizeof(I));
     oref_kkt_ordering(n, m, Pp, Pi, Ap, Ai, perm);
     batch_job J;
     memset(&J, 0, sizeof J);
     J.batch = batch; J.n = n; J.m = m; J.nnzA = Ap[n];
+    J.total = batch * (I)(passes > 0 ? passes : 1);
     J.Pp = Pp; J.Pi = Pi; J.Ap = Ap; J.Ai = Ai; J.perm = perm;
     J.Px = Px; J.Ax = Ax; J.l = l; J.u = u; J.x0 = x0; J.settings = settings;
     J.x = x; J.y = y; J.exit_code = exit_code; J.iters = iters; J.rho_updates = rho_updates;
     if (nthreads <= 0) nthreads = oref_max_threads();
-    if ((I)nthreads > batch) nthreads = (int)batch;
+    if ((I)nthreads > J.total) nthreads = (int)J.total;
     if (nthreads <= 1) {
         batch_worker(&J);
     } else {
@@ -1118,4 +1122,12 @@ int oref_solve_batch(I batch, I n, I m, const I *Pp, const I *Pi, const double *
     }
     free(perm);
     return J.fail;
+}
+
+int oref_solve_batch(I batch, I n, I m, const I *Pp, const I *Pi, const double *Px, const I *Ap,
+                     const I *Ai, const double *Ax, const double *l, const double *u,
+                     const double *x0, const oref_settings *settings, int nthreads, double *x,
+                     double *y, int *exit_code, int *iters, int *rho_updates) {
+    return oref_solve_batch_passes(batch, n, m, Pp, Pi, Px, Ap, Ai, Ax, l, u, x0, settings, nthreads, 1, x, y, exit_code, iters,
+                                   rho_updates);
 }

@@ -120,6 +120,12 @@ int oref_solve_batch(oref_int batch, oref_int n, oref_int m, const oref_int *Pp,
                      const oref_int *Ai, const double *Ax, const double *l, const double *u,
                      const double *x0, const oref_settings *settings, int nthreads,
                      double *x, double *y, int *exit_code, int *iters, int *rho_updates);
+/* the same, `passes` passes over the batch as one continuous work queue (item w solves QP w % batch) */
+int oref_solve_batch_passes(oref_int batch, oref_int n, oref_int m, const oref_int *Pp,
+                     const oref_int *Pi, const double *Px, const oref_int *Ap,
+                     const oref_int *Ai, const double *Ax, const double *l, const double *u,
+                     const double *x0, const oref_settings *settings, int nthreads, int passes,
+                     double *x, double *y, int *exit_code, int *iters, int *rho_updates);
 
 int oref_max_threads(void);
 

@@ -75,6 +75,10 @@ def lib():
     L.oref_solve_batch.argtypes = [C.c_longlong, C.c_longlong, C.c_longlong, _pi, _pi, _pd, _pi, _pi,
                                    _pd, _pd, _pd, C.c_void_p, C.POINTER(Settings), C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.oref_solve_batch_passes.restype = C.c_int
+    L.oref_solve_batch_passes.argtypes = [C.c_longlong, C.c_longlong, C.c_longlong, _pi, _pi, _pd, _pi, _pi,
+                                          _pd, _pd, _pd, C.c_void_p, C.POINTER(Settings), C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.oref_max_threads.restype = C.c_int
     _lib = L
     return L
@@ -187,10 +191,11 @@ def kkt_ordering(n, m, Pp, Pi, Ap, Ai):
     return perm
 
 
-def solve_batch(n, m, P, A_pattern, Ax, l, u, x0=None, settings=None, nthreads=0, want_y=False):
+def solve_batch(n, m, P, A_pattern, Ax, l, u, x0=None, settings=None, nthreads=0, want_y=False, passes=1):
     """Cold setup + warm_start_x + solve for every problem of a batch that shares (P, pattern(A)).
 
     Ax: [batch, nnzA], l/u: [batch, m], x0: [batch, n] or None.
+    passes > 1: that many passes over the batch as one continuous work queue (bench.py's CPU arm).
     Returns dict(x, y, exit_code, iters, rho_updates)."""
     L = lib()
     Pp, Pi, Px = _csc(P)
@@ -209,8 +214,8 @@ def solve_batch(n, m, P, A_pattern, Ax, l, u, x0=None, settings=None, nthreads=0
     if x0 is not None:
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         x0p = x0.ctypes.data
-    rc = L.oref_solve_batch(batch, n, m, Pp, Pi, Px, Ap, Ai, Ax, l, u, x0p, C.byref(settings), nthreads,
-                            x.ctypes.data, y.ctypes.data if want_y else None, code.ctypes.data,
+    rc = L.oref_solve_batch_passes(batch, n, m, Pp, Pi, Px, Ap, Ai, Ax, l, u, x0p, C.byref(settings), nthreads, int(passes),
+                                   x.ctypes.data, y.ctypes.data if want_y else None, code.ctypes.data,
                             iters.ctypes.data, rup.ctypes.data)
     if rc:
         raise ValueError("oref_solve_batch: a setup failed")

@@ -138,8 +138,25 @@ __global__ void peak_fp64_kernel(double *out, int iters) {
 }
 // Work-queue order for a warm re-solve: problems in descending order of the iterations their previous solve took
 // (bucketed), so that the few long solves of a batch start first instead of forming its tail.  One CTA.
-__global__ void order_by_iters_kernel(const int *__restrict__ iters, int n, int *__restrict__ order) {
+// The same kernel maps OSQP's status_val to osqp-cpp's OsqpExitCode so that results can be handed
+// to a device consumer without a host round trip.
+__device__ __forceinline__ int exit_code_of(int status) {
+    switch (status) {
+    case 1: return GOMP_EXIT_OPTIMAL;
+    case 2: return GOMP_EXIT_OPTIMAL_INACCURATE;
+    case -3: return GOMP_EXIT_PRIMAL_INFEASIBLE;
+    case 3: return GOMP_EXIT_PRIMAL_INFEASIBLE_INACCURATE;
+    case -4: return GOMP_EXIT_DUAL_INFEASIBLE;
+    case 4: return GOMP_EXIT_DUAL_INFEASIBLE_INACCURATE;
+    case -2: return GOMP_EXIT_MAX_ITERATIONS;
+    case -7: return GOMP_EXIT_NON_CONVEX;
+    default: return GOMP_EXIT_UNKNOWN;
+    }
+}
+__global__ void order_by_iters_kernel(const int *__restrict__ iters, const int *__restrict__ status, int n, int *__restrict__ order,
+                                      int *__restrict__ code) {
     __shared__ int hist[257], base[257];
+    for (int b = threadIdx.x; b < n; b += blockDim.x) code[b] = exit_code_of(status[b]);
     for (int k = threadIdx.x; k < 257; k += blockDim.x) hist[k] = 0;
     __syncthreads();
     auto bucket = [](int it) { return 255 - min(255, max(0, it) >> 4); }; // long solves -> low bucket index -> front of the queue
@@ -219,12 +236,11 @@ struct gomp_batch {
     // per-batch storage
     DevArray<double> d_A, d_l, d_u, d_q, d_x0, d_xs, d_zs, d_ys, d_rho, d_E, d_D, d_qs, d_dy, d_dx, d_Lg, d_Ug, d_xo, d_yo, d_pri, d_dua, d_obj;
     DevArray<unsigned long long> d_prof;
-    DevArray<int> d_status, d_iters, d_rup, d_counter, d_active, d_order;
+    DevArray<int> d_status, d_iters, d_rup, d_counter, d_active, d_order, d_code;
     bool order_valid = false; // d_order holds the order derived from the previous solve of the same problems
     const int *active_src = nullptr; // per-QP mask of the next solves (device), NULL = all
     const double *A_src = nullptr, *l_src = nullptr, *u_src = nullptr, *q_src = nullptr; // borrowed device inputs
     long long A_pitch = 0;
-    std::vector<int> h_status;
 };
 
 namespace {
@@ -335,6 +351,22 @@ int upload_pattern(gomp_batch *h) {
     return GOMP_OK;
 }
 
+// l <= u everywhere (host arrays), on a few threads
+bool bounds_ordered(const double *l, const double *u, size_t total) {
+    const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, std::thread::hardware_concurrency()), total / 65536 + 1));
+    std::atomic<int> bad{0};
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; ++t)
+        pool.emplace_back([&, t]() {
+            const size_t a = total * t / nt, b = total * (t + 1) / nt;
+            int any = 0;
+            for (size_t k = a; k < b; ++k) any |= (l[k] > u[k]);
+            if (any) bad.store(1);
+        });
+    for (auto &th : pool) th.join();
+    return bad.load() == 0;
+}
+
 // copy (or borrow) one input array; `dst` is allocated lazily
 int stage_input(gomp_batch *h, const double *src, DevArray<double> &dst, size_t count, const double **use) {
     if (!src) return GOMP_OK;
@@ -363,21 +395,8 @@ int load_data(gomp_batch *h, const double *A_val, const double *l, const double 
     CUDA_TRY(cudaSetDevice(h->device));
     if (cold && (!A_val || !l || !u)) return fail(GOMP_ERR_INVALID_ARGUMENT, "setup needs A_val, l and u");
     // bounds validation (OSQP validate_data / osqp_update_bounds: l <= u) on host inputs
-    if (l && u && !is_device_pointer(l) && !is_device_pointer(u)) {
-        const size_t total = B * (size_t)s.m;
-        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, std::thread::hardware_concurrency()), total / 65536 + 1));
-        std::atomic<int> bad{0};
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nt; ++t)
-            pool.emplace_back([&, t]() {
-                const size_t a = total * t / nt, b = total * (t + 1) / nt;
-                int any = 0;
-                for (size_t k = a; k < b; ++k) any |= (l[k] > u[k]);
-                if (any) bad.store(1);
-            });
-        for (auto &th : pool) th.join();
-        if (bad.load()) return fail(GOMP_ERR_INVALID_ARGUMENT, "lower bound exceeds upper bound");
-    }
+    if (l && u && !is_device_pointer(l) && !is_device_pointer(u) && !bounds_ordered(l, u, B * (size_t)s.m))
+        return fail(GOMP_ERR_INVALID_ARGUMENT, "lower bound exceeds upper bound");
     CUDA_TRY(cudaEventRecord(h->evc0, h->stream));
     int rc;
     if ((rc = stage_input(h, A_val, h->d_A, B * (size_t)s.nnzA, &h->A_src))) return rc;
@@ -505,7 +524,7 @@ int gomp_batch_destroy(gomp_batch *h) {
     h->d_yo.release(); h->d_pri.release(); h->d_dua.release(); h->d_obj.release();
     h->d_rell.release(); h->d_cell.release(); h->d_pell.release(); h->d_cpos.release();
     h->d_ascon.release(); h->d_asocon.release(); h->d_asmeta.release(); h->d_asometa.release();
-    h->d_active.release(); h->d_order.release(); h->d_ws.release(); h->d_row_ell.release(); h->d_col_ell.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
+    h->d_active.release(); h->d_order.release(); h->d_code.release(); h->d_ws.release(); h->d_row_ell.release(); h->d_col_ell.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evc0) cudaEventDestroy(h->evc0);
@@ -522,12 +541,20 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     *out = nullptr;
     if (batch <= 0 || n <= 0 || m < 0 || !P_colptr || !A_colptr) return fail(GOMP_ERR_INVALID_ARGUMENT, "bad dimensions or null pattern");
     if (batch > 0x7fffffff) return fail(GOMP_ERR_INVALID_ARGUMENT, "batch too large for one handle");
-    if (gomp_device_count() <= 0) return fail(GOMP_ERR_NO_DEVICE, "no CUDA device visible: libgomp_cuda has no CPU fallback");
     gomp_settings st;
     if (settings) st = *settings;
     else gomp_settings_default(&st);
     if (st.check_termination < 0 || st.max_iter <= 0 || st.scaling < 0 || st.rho <= 0 || st.sigma <= 0 || st.alpha <= 0 || st.alpha >= 2)
         return fail(GOMP_ERR_INVALID_ARGUMENT, "invalid OSQP settings");
+    // settings the kernels do not implement are refused instead of being ignored
+    if (st.adaptive_rho && (st.adaptive_rho_interval <= 0 || (st.check_termination > 0 && st.adaptive_rho_interval % st.check_termination != 0)))
+        return fail(GOMP_ERR_INVALID_ARGUMENT, "adaptive_rho_interval must be > 0 and a multiple of check_termination (OSQP's wall-clock-derived "
+                                               "interval, the meaning of 0 there, is machine dependent and not reproduced)");
+    if (st.adaptive_rho && st.adaptive_rho_tolerance < 1.0) return fail(GOMP_ERR_INVALID_ARGUMENT, "adaptive_rho_tolerance must be >= 1");
+    if (!st.warm_start)
+        return fail(GOMP_ERR_UNSUPPORTED, "warm_start = 0 is not supported: iterates persist across the solves of a handle; gomp_batch_setup is the cold start");
+    if (st.threads_per_cta != 0) return fail(GOMP_ERR_UNSUPPORTED, "threads_per_cta is fixed per back end; leave it 0");
+    if (gomp_device_count() <= 0) return fail(GOMP_ERR_NO_DEVICE, "no CUDA device visible: libgomp_cuda has no CPU fallback");
     if (st.linsys == GOMP_LINSYS_PCG)
         return fail(GOMP_ERR_UNSUPPORTED, "the PCG back end is not built: long horizons use the exact streamed block-tridiagonal "
                                           "factorisation (GOMP_LINSYS_BLOCKTRI_GLOBAL), which keeps OSQP's iteration counts");
@@ -876,7 +903,8 @@ int gomp_batch_solve(gomp_batch *h) {
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     // queue order of the next solve, should it be a warm re-solve of the same problems (gomp_batch_update)
     if (!h->d_order.p) CUDA_TRY(h->d_order.alloc((size_t)h->batch));
-    order_by_iters_kernel<<<1, 1024, 0, h->stream>>>(h->d_iters.p, (int)h->batch, h->d_order.p);
+    if (!h->d_code.p) CUDA_TRY(h->d_code.alloc((size_t)h->batch));
+    order_by_iters_kernel<<<1, 1024, 0, h->stream>>>(h->d_iters.p, h->d_status.p, (int)h->batch, h->d_order.p, h->d_code.p);
     CUDA_TRY(cudaGetLastError());
     h->order_valid = true;
     h->launches += 2; // the ADMM kernel and the queue-order kernel
@@ -945,42 +973,30 @@ static int copy_out(gomp_batch *h, void *dst, const void *src, size_t bytes) {
     return GOMP_OK;
 }
 
-int gomp_batch_get(gomp_batch *h, double *x, double *y, int32_t *exit_code, int32_t *iters, int32_t *rho_updates) {
-    if (!h) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
-    CUDA_TRY(cudaSetDevice(h->device));
+static int queue_results(gomp_batch *h, double *x, double *y, int32_t *exit_code, int32_t *iters, int32_t *rho_updates) {
     const size_t B = (size_t)h->batch;
     int rc;
+    if (exit_code && !h->d_code.p) return fail(GOMP_ERR_INVALID_ARGUMENT, "no solve has been run on this handle");
     if ((rc = copy_out(h, x, h->d_xo.p, B * (size_t)h->sym.n * sizeof(double)))) return rc;
     if ((rc = copy_out(h, y, h->d_yo.p, B * (size_t)h->sym.m * sizeof(double)))) return rc;
     if ((rc = copy_out(h, iters, h->d_iters.p, B * sizeof(int)))) return rc;
     if ((rc = copy_out(h, rho_updates, h->d_rup.p, B * sizeof(int)))) return rc;
-    if (exit_code) {
-        h->h_status.resize(B);
-        CUDA_TRY(cudaMemcpyAsync(h->h_status.data(), h->d_status.p, B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    }
+    if ((rc = copy_out(h, exit_code, h->d_code.p, B * sizeof(int)))) return rc;
+    return GOMP_OK;
+}
+
+int gomp_batch_get_async(gomp_batch *h, double *x, double *y, int32_t *exit_code, int32_t *iters, int32_t *rho_updates) {
+    if (!h) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return queue_results(h, x, y, exit_code, iters, rho_updates);
+}
+
+int gomp_batch_get(gomp_batch *h, double *x, double *y, int32_t *exit_code, int32_t *iters, int32_t *rho_updates) {
+    if (!h) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = queue_results(h, x, y, exit_code, iters, rho_updates))) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (exit_code) {
-        // OSQP status_val -> osqp-cpp OsqpExitCode
-        std::vector<int32_t> code(B);
-        for (size_t b = 0; b < B; ++b) {
-            switch (h->h_status[b]) {
-            case 1: code[b] = GOMP_EXIT_OPTIMAL; break;
-            case 2: code[b] = GOMP_EXIT_OPTIMAL_INACCURATE; break;
-            case -3: code[b] = GOMP_EXIT_PRIMAL_INFEASIBLE; break;
-            case 3: code[b] = GOMP_EXIT_PRIMAL_INFEASIBLE_INACCURATE; break;
-            case -4: code[b] = GOMP_EXIT_DUAL_INFEASIBLE; break;
-            case 4: code[b] = GOMP_EXIT_DUAL_INFEASIBLE_INACCURATE; break;
-            case -2: code[b] = GOMP_EXIT_MAX_ITERATIONS; break;
-            case -7: code[b] = GOMP_EXIT_NON_CONVEX; break;
-            default: code[b] = GOMP_EXIT_UNKNOWN; break;
-            }
-        }
-        if (is_device_pointer(exit_code)) {
-            CUDA_TRY(cudaMemcpy(exit_code, code.data(), B * sizeof(int32_t), cudaMemcpyHostToDevice));
-        } else {
-            std::memcpy(exit_code, code.data(), B * sizeof(int32_t));
-        }
-    }
     float ms = 0;
     if (h->launches > 0 && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_solve_ms = ms;
     else cudaGetLastError();
@@ -1047,5 +1063,221 @@ int gomp_batch_info(gomp_batch *h, gomp_info *info) {
     info->smem_bytes_per_check = 8 * (2 * 2 * s.nnzA + 2 * 2 * s.nnzPu + 2 * (int64_t)s.m_used + 2 * s.n);
     return GOMP_OK;
 }
+
+} // extern "C"
+
+// ================================================================================================
+//                          one batch over several GPUs of one process
+// ================================================================================================
+struct MgShard {
+    int device = 0;
+    int64_t count = 0;
+    gomp_batch *h = nullptr;
+    cudaStream_t stream = nullptr; // the shard handle's stream (owned by the handle)
+    double *A = nullptr, *l = nullptr, *u = nullptr, *q = nullptr, *x0 = nullptr; // staged inputs [count, .]
+    double *xo = nullptr, *yo = nullptr;                                         // staged outputs
+    int32_t *ints = nullptr;                                                     // code, iters, rho_updates [3][count]
+    std::vector<int32_t> h_ints;
+};
+struct gomp_mg {
+    std::vector<MgShard> sh;
+    int64_t batch = 0, n = 0, m = 0, nnzA = 0;
+    bool has_q = false;
+};
+
+namespace {
+// rows k, k + G, k + 2G, ... of a [batch, width] array <-> a contiguous [count, width] shard buffer
+int mg_rows_in(const gomp_mg *g, const MgShard &s, int k, double *dst, const double *src, int64_t width) {
+    const size_t G = g->sh.size(), rb = (size_t)width * sizeof(double);
+    CUDA_TRY(cudaMemcpy2DAsync(dst, rb, src + (size_t)k * width, G * rb, rb, (size_t)s.count, cudaMemcpyDefault, s.stream));
+    return GOMP_OK;
+}
+int mg_rows_out(const gomp_mg *g, const MgShard &s, int k, double *dst, const double *src, int64_t width) {
+    const size_t G = g->sh.size(), rb = (size_t)width * sizeof(double);
+    CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)k * width, G * rb, src, rb, rb, (size_t)s.count, cudaMemcpyDefault, s.stream));
+    return GOMP_OK;
+}
+int mg_stage(gomp_mg *g, MgShard &s, int k, double **buf, const double *src, int64_t width) {
+    if (!src) return GOMP_OK;
+    if (!*buf) CUDA_TRY(cudaMalloc((void **)buf, (size_t)std::max<int64_t>(1, s.count * width) * sizeof(double)));
+    return mg_rows_in(g, s, k, *buf, src, width);
+}
+int mg_load(gomp_mg *g, const double *A_val, const double *l, const double *u, const double *q, bool cold) {
+    if (!g) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
+    if (cold && (!A_val || !l || !u)) return fail(GOMP_ERR_INVALID_ARGUMENT, "setup needs A_val, l and u");
+    if ((l == nullptr) != (u == nullptr)) return fail(GOMP_ERR_INVALID_ARGUMENT, "l and u must be given together");
+    if (l && u && !is_device_pointer(l) && !is_device_pointer(u) && !bounds_ordered(l, u, (size_t)g->batch * (size_t)g->m))
+        return fail(GOMP_ERR_INVALID_ARGUMENT, "lower bound exceeds upper bound");
+    for (size_t k = 0; k < g->sh.size(); ++k) {
+        MgShard &s = g->sh[k];
+        if (s.count == 0) continue;
+        CUDA_TRY(cudaSetDevice(s.device));
+        int rc;
+        if ((rc = mg_stage(g, s, (int)k, &s.A, A_val, g->nnzA))) return rc;
+        if ((rc = mg_stage(g, s, (int)k, &s.l, l, g->m))) return rc;
+        if ((rc = mg_stage(g, s, (int)k, &s.u, u, g->m))) return rc;
+        if ((rc = mg_stage(g, s, (int)k, &s.q, q, g->n))) return rc;
+        // the shard handle borrows the staged arrays (settings.borrow_inputs = 1): no second copy
+        rc = cold ? gomp_batch_setup(s.h, s.A, s.l, s.u, q ? s.q : nullptr)
+                  : gomp_batch_update(s.h, A_val ? s.A : nullptr, l ? s.l : nullptr, u ? s.u : nullptr, q ? s.q : nullptr);
+        if (rc) return rc;
+    }
+    return GOMP_OK;
+}
+} // namespace
+
+extern "C" {
+
+int gomp_mg_destroy(gomp_mg *g) {
+    if (!g) return GOMP_OK;
+    for (MgShard &s : g->sh) {
+        cudaSetDevice(s.device);
+        if (s.h) gomp_batch_destroy(s.h);
+        for (double *p : {s.A, s.l, s.u, s.q, s.x0, s.xo, s.yo})
+            if (p) cudaFree(p);
+        if (s.ints) cudaFree(s.ints);
+    }
+    delete g;
+    return GOMP_OK;
+}
+
+int gomp_mg_create(gomp_mg **out, const gomp_settings *settings, const int32_t *devices, int32_t n_devices, int64_t batch, int64_t n,
+                   int64_t m, const int64_t *P_colptr, const int64_t *P_rowidx, const double *P_val, const int64_t *A_colptr,
+                   const int64_t *A_rowidx) {
+    if (!out) return fail(GOMP_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (batch <= 0 || n <= 0 || !A_colptr) return fail(GOMP_ERR_INVALID_ARGUMENT, "bad dimensions or null pattern");
+    const int visible = gomp_device_count();
+    if (visible <= 0) return fail(GOMP_ERR_NO_DEVICE, "no CUDA device visible: libgomp_cuda has no CPU fallback");
+    if (n_devices <= 0) {
+        n_devices = visible;
+        devices = nullptr;
+    }
+    gomp_mg *g = new gomp_mg();
+    g->batch = batch; g->n = n; g->m = m; g->nnzA = A_colptr[n];
+    g->sh.resize((size_t)n_devices);
+    gomp_settings st;
+    if (settings) st = *settings;
+    else gomp_settings_default(&st);
+    st.stream = nullptr;
+    st.borrow_inputs = 1;
+    for (int k = 0; k < n_devices; ++k) {
+        MgShard &s = g->sh[(size_t)k];
+        s.device = devices ? devices[k] : k;
+        if (s.device < 0 || s.device >= visible) {
+            gomp_mg_destroy(g);
+            return fail(GOMP_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+        }
+        s.count = batch > k ? (batch - k + n_devices - 1) / n_devices : 0;
+        if (s.count == 0) continue;
+        st.device = s.device;
+        int rc = gomp_batch_create(&s.h, &st, s.count, n, m, P_colptr, P_rowidx, P_val, A_colptr, A_rowidx, nullptr, nullptr, nullptr, nullptr);
+        if (rc) {
+            std::string keep = g_error;
+            gomp_mg_destroy(g);
+            return fail(rc, keep);
+        }
+        void *stream = nullptr;
+        gomp_batch_device_views(s.h, nullptr, nullptr, nullptr, nullptr, &stream);
+        s.stream = (cudaStream_t)stream;
+    }
+    // peer access between the devices of the handle (device-pointer inputs / outputs living on another GPU); not fatal when absent:
+    // cudaMemcpyDefault then stages through the host
+    for (const MgShard &a : g->sh)
+        for (const MgShard &b : g->sh)
+            if (a.device != b.device) {
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, a.device, b.device) == cudaSuccess && can) {
+                    cudaSetDevice(a.device);
+                    cudaDeviceEnablePeerAccess(b.device, 0);
+                }
+                cudaGetLastError();
+            }
+    *out = g;
+    return GOMP_OK;
+}
+
+int gomp_mg_setup(gomp_mg *g, const double *A_val, const double *l, const double *u, const double *q) { return mg_load(g, A_val, l, u, q, true); }
+
+int gomp_mg_update(gomp_mg *g, const double *A_val, const double *l, const double *u, const double *q) { return mg_load(g, A_val, l, u, q, false); }
+
+int gomp_mg_warm_start_x(gomp_mg *g, const double *x0) {
+    if (!g || !x0) return fail(GOMP_ERR_INVALID_ARGUMENT, "null argument");
+    for (size_t k = 0; k < g->sh.size(); ++k) {
+        MgShard &s = g->sh[k];
+        if (s.count == 0) continue;
+        CUDA_TRY(cudaSetDevice(s.device));
+        int rc;
+        if ((rc = mg_stage(g, s, (int)k, &s.x0, x0, g->n))) return rc;
+        if ((rc = gomp_batch_warm_start_x(s.h, s.x0))) return rc;
+    }
+    return GOMP_OK;
+}
+
+int gomp_mg_solve(gomp_mg *g) {
+    if (!g) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
+    for (MgShard &s : g->sh)
+        if (s.count)
+            if (int rc = gomp_batch_solve(s.h)) return rc;
+    return GOMP_OK;
+}
+
+int gomp_mg_get(gomp_mg *g, double *x, double *y, int32_t *exit_code, int32_t *iters, int32_t *rho_updates) {
+    if (!g) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
+    const size_t G = g->sh.size();
+    const bool want_ints = exit_code || iters || rho_updates;
+    // queue every shard's copies first, then wait: the shards' transfers overlap
+    for (size_t k = 0; k < G; ++k) {
+        MgShard &s = g->sh[k];
+        if (s.count == 0) continue;
+        CUDA_TRY(cudaSetDevice(s.device));
+        const double *xo = nullptr;
+        gomp_batch_device_views(s.h, nullptr, nullptr, nullptr, &xo, nullptr);
+        int rc;
+        if (x && (rc = mg_rows_out(g, s, (int)k, x, xo, g->n))) return rc;
+        if (y) {
+            if (!s.yo) CUDA_TRY(cudaMalloc((void **)&s.yo, (size_t)s.count * (size_t)g->m * sizeof(double)));
+            if ((rc = gomp_batch_get_async(s.h, nullptr, s.yo, nullptr, nullptr, nullptr))) return rc;
+            if ((rc = mg_rows_out(g, s, (int)k, y, s.yo, g->m))) return rc;
+        }
+        if (want_ints) {
+            if (!s.ints) CUDA_TRY(cudaMalloc((void **)&s.ints, (size_t)s.count * 3 * sizeof(int32_t)));
+            if ((rc = gomp_batch_get_async(s.h, nullptr, nullptr, s.ints, s.ints + s.count, s.ints + 2 * s.count))) return rc;
+            s.h_ints.resize((size_t)s.count * 3);
+            CUDA_TRY(cudaMemcpyAsync(s.h_ints.data(), s.ints, (size_t)s.count * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        }
+    }
+    for (MgShard &s : g->sh)
+        if (s.count)
+            if (int rc = gomp_batch_sync(s.h)) return rc;
+    if (want_ints) {
+        // 4-byte rows: interleaved on the host (one strided copy per row would be slower than the solve)
+        int32_t *dst[3] = {exit_code, iters, rho_updates};
+        for (int a = 0; a < 3; ++a) {
+            if (!dst[a]) continue;
+            std::vector<int32_t> tmp;
+            int32_t *out = dst[a];
+            const bool dev = is_device_pointer(out);
+            if (dev) {
+                tmp.resize((size_t)g->batch);
+                out = tmp.data();
+            }
+            for (size_t k = 0; k < G; ++k)
+                for (int64_t i = 0; i < g->sh[k].count; ++i) out[(size_t)i * G + k] = g->sh[k].h_ints[(size_t)a * g->sh[k].count + i];
+            if (dev) CUDA_TRY(cudaMemcpy(dst[a], tmp.data(), (size_t)g->batch * sizeof(int32_t), cudaMemcpyDefault));
+        }
+    }
+    return GOMP_OK;
+}
+
+int gomp_mg_shard(gomp_mg *g, int32_t k, gomp_batch **handle, int32_t *device, int64_t *count) {
+    if (!g || k < 0 || (size_t)k >= g->sh.size()) return fail(GOMP_ERR_INVALID_ARGUMENT, "bad shard index");
+    if (handle) *handle = g->sh[(size_t)k].h;
+    if (device) *device = g->sh[(size_t)k].device;
+    if (count) *count = g->sh[(size_t)k].count;
+    return GOMP_OK;
+}
+
+int gomp_mg_num_shards(gomp_mg *g) { return g ? (int)g->sh.size() : 0; }
 
 } // extern "C"

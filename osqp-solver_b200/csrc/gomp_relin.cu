@@ -43,7 +43,10 @@ struct SceneDev {
     Ball ball[2];
     double box_lo[3], box_hi[3];
     gomp::ArmGeometry geo;
-    const double *lines;  // [count][O][5]
+    double *lines;        // [count][O][5]
+    const double *tA, *tl, *tu; // template of one problem (gomp_device_scene_set_template): everything but the start / goal rows
+                                // and the Cartesian rows is the same for every problem of a configuration
+    int pos_row0;         // row of (waypoint 0, joint 0) of the position box rows
     const int32_t *rows;  // [n_rows]
     const int32_t *kidx;  // [n_rows][N]
 };
@@ -153,6 +156,70 @@ __global__ void relin_kernel(const SceneDev S, const double *__restrict__ x, con
     }
 }
 
+// ---- gomp_problem_generate on the device (reference src/gomp-solver.h:57-64 initConstraints + build, :105-116 warm start) ----
+// What makeTrajectoryConstraints (trajectory-constraints.h) writes depends on the problem in three places only: the rows that pin
+// waypoint 0 to the start and waypoint W-3 to the goal, the Cartesian rows (relin_kernel around the warm start) and the warm
+// start itself.  One thread per output element: A_val / l / u from the template with the pinned rows overwritten, x0 = [linspace
+// (start, goal, W) | 0] with the arithmetic of utils.h linspace.
+__global__ void assemble_fill_kernel(const SceneDev S, const double *__restrict__ sg, double *A_val, double *l, double *u, double *x0) {
+    const long long per = S.nnzA + 2 * S.m + S.n;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S.count * per) return;
+    const long long prob = idx / per;
+    long long e = idx - prob * per;
+    const double *start = sg + (size_t)prob * 2 * S.N, *goal = start + S.N;
+    if (e < S.nnzA) {
+        A_val[(size_t)prob * S.nnzA + e] = S.tA[e];
+        return;
+    }
+    e -= S.nnzA;
+    if (e < 2 * S.m) {
+        const bool upper = e >= S.m;
+        const long long row = upper ? e - S.m : e;
+        double v = upper ? S.tu[row] : S.tl[row];
+        const long long r0 = row - S.pos_row0, rg = r0 - (long long)(S.W - 3) * S.N;
+        if (r0 >= 0 && r0 < S.N) v = start[r0];      // position(0, equal(start))
+        else if (rg >= 0 && rg < S.N) v = goal[rg];  // position(W - 3, equal(goal))
+        (upper ? u : l)[(size_t)prob * S.m + row] = v;
+        return;
+    }
+    e -= 2 * S.m;
+    double v = 0.0;
+    if (e < (long long)S.W * S.N) {
+        const int w = (int)(e / S.N), j = (int)(e - (long long)w * S.N);
+        const double step = (goal[j] - start[j]) / (double)(S.W - 1);
+        v = step * (double)w + start[j];
+    }
+    x0[(size_t)prob * S.n + e] = v;
+}
+
+// obstacle lines of a problem from its start and goal (gomp_host.cpp drawInstance): line k is perpendicular to the start->goal
+// chord of the gripper (XY), crosses it at (k+1)/(O+1), kLineDrop below the higher end point
+template <int N>
+__global__ void assemble_lines_kernel(const SceneDev S, const double *__restrict__ sg) {
+    const long long prob = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (prob >= S.count) return;
+    const Ball g = S.ball[S.n_balls - 1]; // the gripper is listed last
+    double ps[3], pg[3];
+    gomp::armPoint<N>(S.geo, sg + (size_t)prob * 2 * N, g.upto, g.offset, ps);
+    gomp::armPoint<N>(S.geo, sg + (size_t)prob * 2 * N + N, g.upto, g.offset, pg);
+    double dx = pg[0] - ps[0], dy = pg[1] - ps[1];
+    if (sqrt(dx * dx + dy * dy) < 1e-9) {
+        dx = 1.0;
+        dy = 0.0;
+    }
+    const double vx = -dy, vy = dx, len = sqrt(vx * vx + vy * vy);
+    for (int k = 0; k < S.O; ++k) {
+        const double f = (double)(k + 1) / (double)(S.O + 1);
+        double *o = S.lines + ((size_t)prob * S.O + k) * 5;
+        o[0] = vx / len;
+        o[1] = vy / len;
+        o[2] = ps[0] + f * (pg[0] - ps[0]);
+        o[3] = ps[1] + f * (pg[1] - ps[1]);
+        o[4] = fmax(ps[2], pg[2]) - 0.15; // kLineDrop
+    }
+}
+
 __global__ void fill_kernel(int32_t *ok, long long count, int32_t v) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) ok[i] = v;
@@ -203,6 +270,7 @@ struct gomp_device_scene {
     int device = 0;
     double *lines = nullptr;
     int32_t *rows = nullptr, *kidx = nullptr;
+    double *tmpl = nullptr; // [nnzA + 2 m]
 };
 
 extern "C" {
@@ -213,13 +281,14 @@ int gomp_device_scene_destroy(gomp_device_scene *s) {
     if (s->lines) cudaFree(s->lines);
     if (s->rows) cudaFree(s->rows);
     if (s->kidx) cudaFree(s->kidx);
+    if (s->tmpl) cudaFree(s->tmpl);
     delete s;
     return 0;
 }
 
 int gomp_device_scene_create(gomp_device_scene **out, const gomp_problem_config *cfg, int64_t count, int64_t n, int64_t m, int64_t nnzA,
                              const double *lines, int64_t n_rows, const int32_t *rows, const int32_t *kidx, int32_t device) {
-    if (!out || !cfg || count <= 0 || !rows || !kidx || (cfg->n_obstacles > 0 && !lines)) return 1;
+    if (!out || !cfg || count <= 0 || !rows || !kidx) return 1; // lines == NULL: filled in by gomp_device_assemble
     if (cfg->n_dim < 2 || cfg->n_dim > 7 || cfg->n_balls < 1 || cfg->n_balls > 2) return 1;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return 3; // no CPU fallback
@@ -252,7 +321,7 @@ int gomp_device_scene_create(gomp_device_scene **out, const gomp_problem_config 
     const size_t lb = (size_t)count * std::max(1, d.O) * 5 * sizeof(double);
     bool ok = cudaMalloc((void **)&s->lines, lb) == cudaSuccess && cudaMalloc((void **)&s->rows, (size_t)n_rows * 4) == cudaSuccess &&
               cudaMalloc((void **)&s->kidx, (size_t)n_rows * N * 4) == cudaSuccess;
-    if (ok && d.O > 0) ok = cudaMemcpy(s->lines, lines, (size_t)count * d.O * 5 * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && d.O > 0 && lines) ok = cudaMemcpy(s->lines, lines, (size_t)count * d.O * 5 * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
     if (ok) ok = cudaMemcpy(s->rows, rows, (size_t)n_rows * 4, cudaMemcpyHostToDevice) == cudaSuccess;
     if (ok) ok = cudaMemcpy(s->kidx, kidx, (size_t)n_rows * N * 4, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
@@ -260,6 +329,8 @@ int gomp_device_scene_create(gomp_device_scene **out, const gomp_problem_config 
         return 4;
     }
     d.lines = s->lines; d.rows = s->rows; d.kidx = s->kidx;
+    d.tA = d.tl = d.tu = nullptr;
+    d.pos_row0 = N * (d.W - 1); // after the N (W - 1) dynamics rows (constraint-builder.h row layout; gomp_host.cpp cartRows)
     *out = s;
     return 0;
 }
@@ -284,6 +355,37 @@ int gomp_device_relinearize(gomp_device_scene *s, const double *x, const double 
     const unsigned grid = (unsigned)((total + block - 1) / block);
     RELIN_DISPATCH(relin_kernel, s->d, x, x_fallback, A_val, l, u)
     return cudaGetLastError() == cudaSuccess ? 0 : 4;
+}
+
+int gomp_device_scene_set_template(gomp_device_scene *s, const double *A_val, const double *l, const double *u) {
+    if (!s || !A_val || !l || !u) return 1;
+    if (cudaSetDevice(s->device) != cudaSuccess) return 4;
+    const size_t na = (size_t)s->d.nnzA, m = (size_t)s->d.m;
+    if (!s->tmpl && cudaMalloc((void **)&s->tmpl, (na + 2 * m) * sizeof(double)) != cudaSuccess) return 4;
+    if (cudaMemcpy(s->tmpl, A_val, na * sizeof(double), cudaMemcpyDefault) != cudaSuccess ||
+        cudaMemcpy(s->tmpl + na, l, m * sizeof(double), cudaMemcpyDefault) != cudaSuccess ||
+        cudaMemcpy(s->tmpl + na + m, u, m * sizeof(double), cudaMemcpyDefault) != cudaSuccess)
+        return 4;
+    s->d.tA = s->tmpl; s->d.tl = s->tmpl + na; s->d.tu = s->tmpl + na + m;
+    return 0;
+}
+
+int gomp_device_assemble(gomp_device_scene *s, const double *start_goal, double *A_val, double *l, double *u, double *x0, void *stream) {
+    if (!s || !start_goal || !A_val || !l || !u || !x0) return 1;
+    if (!s->d.tA) return 1; // gomp_device_scene_set_template first
+    if (cudaSetDevice(s->device) != cudaSuccess) return 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int block = 256;
+    {
+        const long long total = s->d.count * (s->d.nnzA + 2 * s->d.m + s->d.n);
+        assemble_fill_kernel<<<(unsigned)((total + block - 1) / block), block, 0, st>>>(s->d, start_goal, A_val, l, u, x0);
+    }
+    if (s->d.O > 0) {
+        const unsigned grid = (unsigned)((s->d.count + block - 1) / block);
+        RELIN_DISPATCH(assemble_lines_kernel, s->d, start_goal)
+    }
+    if (cudaGetLastError() != cudaSuccess) return 4;
+    return gomp_device_relinearize(s, x0, nullptr, A_val, l, u, stream); // withObstacles around the warm start
 }
 
 int gomp_device_check(gomp_device_scene *s, const double *x, int32_t *ok, void *stream) {

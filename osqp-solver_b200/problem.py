@@ -137,6 +137,17 @@ def fk(cfg, q, ball=0, want_jac=False):
     return (xyz, jac) if want_jac else xyz
 
 
+def start_goal(pattern, first_id, count, nthreads=0, out=None):
+    """start / goal joint vectors of the problems only: [count, 2N] (what device-side assembly needs from the host)."""
+    cfg = pattern.cfg
+    sg = out if out is not None else np.empty((count, 2 * cfg.n_dim), dtype=np.float64)
+    assert sg.shape == (count, 2 * cfg.n_dim) and sg.dtype == np.float64 and sg.flags.c_contiguous
+    rc = lib().gomp_problem_generate(C.byref(cfg), C.c_int64(first_id), C.c_int64(count), None, None, None, None, _p(sg), C.c_int32(nthreads))
+    if rc:
+        raise ValueError("gomp_problem_generate failed")
+    return sg
+
+
 def scene(pattern, first_id, count):
     """Obstacle lines of the problems: [count, n_obstacles, 5] = unit direction (x, y), point (x, y, z)."""
     cfg = pattern.cfg
@@ -168,10 +179,11 @@ class DeviceScene:
     Arguments of relinearize / check are CUDA torch tensors (or raw device pointers as ints)."""
 
     def __init__(self, pattern, first_id, count, device=-1):
+        """first_id = None: the obstacle lines are not uploaded but derived on the device by `assemble`."""
         from . import solver as _solver
         self._L = _solver.lib()
         self.pattern, self.count = pattern, count
-        lines = scene(pattern, first_id, count)
+        lines = scene(pattern, first_id, count) if first_id is not None else np.zeros((0,))
         rows, kidx = cart_rows(pattern)
         self.h = C.c_void_p()
         rc = self._L.gomp_device_scene_create(C.byref(self.h), C.byref(pattern.cfg), C.c_int64(count), C.c_int64(pattern.n),
@@ -191,6 +203,23 @@ class DeviceScene:
                                              C.c_void_p(stream or 0))
         if rc:
             raise RuntimeError(f"gomp_device_relinearize failed ({rc})")
+
+    def set_template(self, template=None):
+        """(A_val, l, u) of any one problem of the configuration: the problem-independent rows of device-side assembly."""
+        if template is None:
+            template = generate(self.pattern, 0, 1)
+        t = [np.ascontiguousarray(np.asarray(template[k]).reshape(-1), dtype=np.float64) for k in ("A_val", "l", "u")]
+        assert t[0].size == self.pattern.nnzA and t[1].size == self.pattern.m and t[2].size == self.pattern.m
+        rc = self._L.gomp_device_scene_set_template(self.h, _p(t[0]), _p(t[1]), _p(t[2]))
+        if rc:
+            raise RuntimeError(f"gomp_device_scene_set_template failed ({rc})")
+
+    def assemble(self, start_goal, A_val, l, u, x0, stream=None):
+        """gomp_problem_generate on the device: start_goal [count, 2N] -> A_val, l, u, x0 (all CUDA tensors)."""
+        rc = self._L.gomp_device_assemble(self.h, self._dp(start_goal), self._dp(A_val), self._dp(l), self._dp(u), self._dp(x0),
+                                          C.c_void_p(stream or 0))
+        if rc:
+            raise RuntimeError(f"gomp_device_assemble failed ({rc})")
 
     def check(self, x, ok, stream=None):
         rc = self._L.gomp_device_check(self.h, self._dp(x), self._dp(ok), C.c_void_p(stream or 0))

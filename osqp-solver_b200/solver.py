@@ -18,9 +18,14 @@ EXIT_NAMES = ["kOptimal", "kPrimalInfeasible", "kDualInfeasible", "kOptimalInacc
               "kDualInfeasibleInaccurate", "kMaxIterations", "kInterrupted", "kTimeLimitReached", "kNonConvex", "kUnknown"]
 
 EXPORTS = ["gomp_settings_default", "gomp_batch_create", "gomp_batch_setup", "gomp_batch_warm_start_x", "gomp_batch_solve",
-           "gomp_batch_update", "gomp_batch_set_active", "gomp_batch_get", "gomp_batch_get_info", "gomp_batch_info", "gomp_batch_sync",
+           "gomp_batch_update", "gomp_batch_set_active", "gomp_batch_get", "gomp_batch_get_async", "gomp_batch_get_info", "gomp_batch_info", "gomp_batch_sync",
            "gomp_batch_destroy", "gomp_batch_device_views", "gomp_device_malloc", "gomp_device_free", "gomp_device_memcpy",
-           "gomp_measure_peaks", "gomp_last_error_string", "gomp_device_count", "gomp_version"]
+           "gomp_measure_peaks", "gomp_last_error_string", "gomp_device_count", "gomp_version",
+           "gomp_mg_create", "gomp_mg_setup", "gomp_mg_warm_start_x", "gomp_mg_update", "gomp_mg_solve", "gomp_mg_get", "gomp_mg_shard",
+           "gomp_mg_num_shards", "gomp_mg_destroy"]
+# include/gomp_problem.h, device section (same library)
+DEVICE_EXPORTS = ["gomp_device_scene_create", "gomp_device_scene_set_template", "gomp_device_assemble", "gomp_device_relinearize",
+                  "gomp_device_check", "gomp_device_scene_destroy"]
 
 
 class Settings(C.Structure):
@@ -65,7 +70,7 @@ def lib():
         if not os.path.exists(path):
             raise RuntimeError(f"{path} missing: build it with `make -C osqp-solver_b200` (or __graft_entry__.build())")
         L = C.CDLL(path)
-        for name in EXPORTS:
+        for name in EXPORTS + DEVICE_EXPORTS:
             getattr(L, name)  # every symbol of include/gomp_cuda.h must be exported
         L.gomp_last_error_string.restype = C.c_char_p
         L.gomp_version.restype = C.c_char_p
@@ -197,6 +202,11 @@ class BatchQPSolver:
                                     C.c_void_p(rho_updates.ctypes.data)))
         return dict(x=x, y=y, exit_code=exit_code, iters=iters, rho_updates=rho_updates)
 
+    def get_async(self, x=None, y=None, exit_code=None, iters=None, rho_updates=None):
+        """Queue the result copies on the handle's stream without waiting (device tensors / pinned host arrays)."""
+        ptrs = [_ptr(a, dtype=np.float64 if k < 2 else np.int32)[0] for k, a in enumerate((x, y, exit_code, iters, rho_updates))]
+        _check(lib().gomp_batch_get_async(self.h, *ptrs))
+
     def solve(self, want_y=False):
         """QPSolver::solve for the whole batch: run, wait, fetch."""
         self.solve_async()
@@ -215,6 +225,77 @@ class BatchQPSolver:
         out = {k: getattr(inf, k) for k, _ in Info._fields_}
         out["phase_cycles"] = list(inf.phase_cycles)
         return out
+
+
+class MultiGpuSolver:
+    """One batch interleaved over several GPUs of this process (include/gomp_cuda.h, gomp_mg_*): same call surface as
+    BatchQPSolver with whole-batch arrays in the caller's order."""
+
+    def __init__(self, n, m, P_colptr, P_rowidx, P_val, A_colptr, A_rowidx, batch, devices=None, settings=None, var_order=None,
+                 block_size=0):
+        L = lib()
+        self.n, self.m, self.batch = int(n), int(m), int(batch)
+        self.settings = settings if settings is not None else default_settings()
+        self._keep = []
+        if var_order is not None:
+            vo = np.ascontiguousarray(var_order, dtype=np.int64)
+            self._keep.append(vo)
+            self.settings.var_order = vo.ctypes.data
+        if block_size:
+            self.settings.block_size = int(block_size)
+        idx = [np.ascontiguousarray(a, dtype=np.int64) for a in (P_colptr, P_rowidx, A_colptr, A_rowidx)]
+        pv = np.ascontiguousarray(P_val, dtype=np.float64)
+        self._keep += idx + [pv]
+        dv = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        self.h = C.c_void_p()
+        _check(L.gomp_mg_create(C.byref(self.h), C.byref(self.settings), None if dv is None else C.c_void_p(dv.ctypes.data),
+                                C.c_int32(0 if dv is None else len(dv)), C.c_int64(self.batch), C.c_int64(self.n), C.c_int64(self.m),
+                                C.c_void_p(idx[0].ctypes.data), C.c_void_p(idx[1].ctypes.data), C.c_void_p(pv.ctypes.data),
+                                C.c_void_p(idx[2].ctypes.data), C.c_void_p(idx[3].ctypes.data)))
+        self.num_shards = L.gomp_mg_num_shards(self.h)
+
+    def setup(self, A_val, l, u, q=None):
+        ptrs = [_ptr(a) for a in (A_val, l, u, q)]
+        _check(lib().gomp_mg_setup(self.h, *[p[0] for p in ptrs]))
+
+    def update(self, A_val=None, l=None, u=None, q=None):
+        ptrs = [_ptr(a) for a in (A_val, l, u, q)]
+        _check(lib().gomp_mg_update(self.h, *[p[0] for p in ptrs]))
+
+    def set_warm_start(self, x0):
+        p, keep = _ptr(x0)
+        _check(lib().gomp_mg_warm_start_x(self.h, p))
+
+    def solve_async(self):
+        _check(lib().gomp_mg_solve(self.h))
+
+    def get(self, want_y=False):
+        x = np.empty((self.batch, self.n))
+        y = np.empty((self.batch, self.m)) if want_y else None
+        code, iters, rup = (np.empty(self.batch, dtype=np.int32) for _ in range(3))
+        _check(lib().gomp_mg_get(self.h, C.c_void_p(x.ctypes.data), None if y is None else C.c_void_p(y.ctypes.data),
+                                 C.c_void_p(code.ctypes.data), C.c_void_p(iters.ctypes.data), C.c_void_p(rup.ctypes.data)))
+        return dict(x=x, y=y, exit_code=code, iters=iters, rho_updates=rup)
+
+    def solve(self, want_y=False):
+        self.solve_async()
+        return self.get(want_y=want_y)
+
+    def shard(self, k):
+        dev, cnt = C.c_int32(), C.c_int64()
+        _check(lib().gomp_mg_shard(self.h, C.c_int32(k), None, C.byref(dev), C.byref(cnt)))
+        return dev.value, cnt.value
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            lib().gomp_mg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def measure_peaks():

@@ -37,6 +37,19 @@ def test_host_library_exports_header():
         assert hasattr(cuda if s.startswith("gomp_device_") else host, s), s
 
 
+def test_unsupported_settings_are_refused_not_ignored():
+    """warm_start = 0, threads_per_cta and adaptive_rho_interval = 0 used to be silently ignored."""
+    pkg = package()
+    P, S = pkg.problem, pkg.solver
+    pat = P.Pattern(P.default_config(waypoints=8))
+    for kw, code in ((dict(warm_start=0), 4), (dict(threads_per_cta=128), 4), (dict(adaptive_rho_interval=0), 1),
+                     (dict(adaptive_rho_interval=30), 1), (dict(adaptive_rho_tolerance=0.5), 1)):
+        with pytest.raises(S.GompError) as e:
+            S.BatchQPSolver(pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx, batch=2,
+                            settings=S.default_settings(**kw), var_order=pat.var_order, block_size=pat.block_size)
+        assert e.value.code == code, kw
+
+
 def test_settings_defaults_match_osqp():
     pkg = package()
     s = pkg.solver.default_settings()
