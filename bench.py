@@ -380,13 +380,14 @@ def extra_sqp_sequence(pkg, O, torch, batch=4096, rounds=10, cpu_sample=64):
             "all_rounds_status_agreement": float(code_eq), "all_rounds_iterations_agreement": float(iter_eq)}
 
 
-def extra_long_horizon(pkg, O, W=400, batches=(1, 148), cpu_sample=16):
-    """BASELINE.json configs[3]: N=7, H=400 on the streamed back end, batch 1 and one QP per SM, beside the oracle."""
+def extra_long_horizon(pkg, O, W=400, batches=(1, 148), cpu_sample=16, name="BASELINE.json configs[3]", **cfg_kw):
+    """BASELINE.json configs[3]: N=7, H=400 on the streamed back end, batch 1 and one QP per SM, beside the oracle (also used for
+    configs[0], the reference example's shape: N=6, W=802, two balls, no obstacle lines)."""
     P, S = pkg.problem, pkg.solver
-    pat = P.Pattern(P.default_config(waypoints=W))
+    pat = P.Pattern(P.default_config(waypoints=W, **cfg_kw))
     nmax = max(batches)
     d = P.generate(pat, 0, nmax)
-    out = {"workload": f"BASELINE.json configs[3]: N=7, H={W} (n={pat.n}, m={pat.m}, nnzA={pat.nnzA})"}
+    out = {"workload": f"{name}: N={pat.cfg.n_dim}, H={W} (n={pat.n}, m={pat.m}, nnzA={pat.nnzA})"}
     results = None
     for batch in batches:
         sub = {k: d[k][:batch] for k in ("A_val", "l", "u", "x0")}
@@ -703,6 +704,11 @@ def run_gpu(args):
                 extra["long_horizon_h400"] = extra_long_horizon(pkg, O)
             except Exception as e:
                 extra["long_horizon_h400"] = {"error": repr(e)}
+            try:
+                extra["example_shape_n6_w802"] = extra_long_horizon(pkg, O, W=802, batches=(1, 16), cpu_sample=16, n_dim=6, n_balls=2, n_obstacles=0,
+                                                                    name="BASELINE.json configs[0] (examples/solver-example.cpp shape, synthetic chain)")
+            except Exception as e:
+                extra["example_shape_n6_w802"] = {"error": repr(e)}
     line["extra"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:

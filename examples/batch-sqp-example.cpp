@@ -1,6 +1,6 @@
 // batch-sqp-example.cpp -- GOMPSolver::run (one horizon, reference src/gomp-solver.h:57-91) for a batch of the
 // repo's synthetic 7-DoF problems, SQP rounds on the GPU.  Host C++ over the two C ABIs only.
-// Build:  make -C osqp-solver_b200 example      Run:  build/batch-sqp-example [count] [first_id] [max_rounds]
+// Build:  make -C osqp-solver_b200 example      Run:  build/batch-sqp-example [count] [first_id] [max_rounds] [rerun]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +27,10 @@ int main(int argc, char **argv) {
         std::printf("codes");
         for (long long b = 0; b < count && b < 64; ++b) std::printf(" %d:%d", (int)r.exit_code[(size_t)b], (int)r.rounds[(size_t)b]);
         std::printf("\n");
+        if (argc > 4) { // run the same planner again: a run starts over (fresh QPSolver per run in the reference) and must agree
+            GOMPBatchSolver::Result again = planner.run(max_rounds);
+            std::printf("rerun_equal %d\n", (int)(again.exit_code == r.exit_code && again.rounds == r.rounds && again.total_qp_solves == r.total_qp_solves));
+        }
         return 0;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());

@@ -178,6 +178,15 @@ int gomp_batch_get_async(gomp_batch *h, double *x, double *y, int32_t *exit_code
 int gomp_batch_get_info(gomp_batch *h, double *pri_res, double *dua_res, double *rho,
                         double *obj_val);
 
+/* Infeasibility certificates of the last solve, as osqp-cpp hands them out (OsqpSolver::primal_infeasibility_certificate /
+ * dual_infeasibility_certificate; the reference never reads them, src/osqp-wrapper.h:53).  prim_inf_cert [batch, m]: for
+ * a problem that ended (inaccurately) primal infeasible, delta_y of the terminating iteration projected onto the polar of
+ * the recession cone of [l, u], un-scaled and normalised to unit infinity norm (OSQP check_termination + store_solution):
+ * A' v ~ 0 and u' max(v, 0) + l' min(v, 0) < 0.  dual_inf_cert [batch, n]: delta_x likewise for dual infeasible problems
+ * (only possible with q != 0).  Rows of problems with any other status are NaN.  Either pointer may be NULL; host or
+ * device pointers; waits for the handle's stream. */
+int gomp_batch_get_certificates(gomp_batch *h, double *prim_inf_cert, double *dual_inf_cert);
+
 /* Per-problem mask for the following solves: active [batch] int32 (host or device; borrowed when it is a
  * device pointer and settings.borrow_inputs is set), NULL = every problem.  A problem with active == 0 is
  * skipped: its iterates, rho and last results stay untouched.  This is what a batched SQP loop

@@ -1015,6 +1015,15 @@ int oref_solve(oref_solver *s) {
     } else {
         vec_set(s->sol_x, NAN, n);
         vec_set(s->sol_y, NAN, m);
+        /* [MEM: auxil.c store_solution] normalise the infeasibility certificate to unit infinity norm */
+        if (s->status == OREF_PRIMAL_INFEASIBLE || s->status == OREF_PRIMAL_INFEASIBLE_INACCURATE) {
+            double nrm = vec_norm_inf(s->delta_y, m);
+            for (I i = 0; i < m; i++) s->delta_y[i] *= 1.0 / nrm;
+        }
+        if (s->status == OREF_DUAL_INFEASIBLE || s->status == OREF_DUAL_INFEASIBLE_INACCURATE) {
+            double nrm = vec_norm_inf(s->delta_x, n);
+            for (I j = 0; j < n; j++) s->delta_x[j] *= 1.0 / nrm;
+        }
         /* cold start for the next run (iterates cannot restart from NaN) */
         vec_set(s->x, 0.0, n); vec_set(s->z, 0.0, m); vec_set(s->y, 0.0, m);
     }
@@ -1024,6 +1033,10 @@ int oref_solve(oref_solver *s) {
 /* ------------------------------------------------------------------ getters */
 const double *oref_x(const oref_solver *s) { return s->sol_x; }
 const double *oref_y(const oref_solver *s) { return s->sol_y; }
+/* osqp-cpp primal_infeasibility_certificate() / dual_infeasibility_certificate(): work->delta_y / delta_x (meaningful after an
+ * infeasible status only) */
+const double *oref_delta_y(const oref_solver *s) { return s->delta_y; }
+const double *oref_delta_x(const oref_solver *s) { return s->delta_x; }
 int oref_status(const oref_solver *s) { return s->status; }
 int oref_iter(const oref_solver *s) { return s->iter; }
 int oref_rho_updates(const oref_solver *s) { return s->rho_updates; }

@@ -93,7 +93,9 @@ int oref_solve(oref_solver *s);                           /* osqp_solve; returns
 
 /* results of the last solve */
 const double *oref_x(const oref_solver *s);  /* unscaled primal (NaN if infeasible) */
-const double *oref_y(const oref_solver *s);  /* unscaled dual */
+const double *oref_y(const oref_solver *s);
+const double *oref_delta_y(const oref_solver *s); /* infeasibility certificates (after an infeasible status) */
+const double *oref_delta_x(const oref_solver *s);  /* unscaled dual */
 int oref_status(const oref_solver *s);
 int oref_exit_code(const oref_solver *s);    /* osqp-cpp OsqpExitCode value */
 int oref_iter(const oref_solver *s);

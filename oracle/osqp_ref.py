@@ -60,7 +60,7 @@ def lib():
     L.oref_update_A.argtypes = [C.c_void_p, _pd]
     L.oref_update_bounds.argtypes = [C.c_void_p, _pd, _pd]
     L.oref_solve.argtypes = [C.c_void_p]
-    for f in ("oref_x", "oref_y", "oref_D", "oref_E"):
+    for f in ("oref_x", "oref_y", "oref_D", "oref_E", "oref_delta_y", "oref_delta_x"):
         getattr(L, f).restype = C.POINTER(C.c_double)
         getattr(L, f).argtypes = [C.c_void_p]
     for f in ("oref_status", "oref_exit_code", "oref_iter", "oref_rho_updates", "oref_num_factorizations"):
@@ -162,6 +162,14 @@ class Solver:
     @property
     def y(self):
         return np.ctypeslib.as_array(lib().oref_y(self.h), shape=(self.m,)).copy()
+
+    @property
+    def prim_inf_cert(self):
+        return np.ctypeslib.as_array(lib().oref_delta_y(self.h), shape=(self.m,)).copy()
+
+    @property
+    def dual_inf_cert(self):
+        return np.ctypeslib.as_array(lib().oref_delta_x(self.h), shape=(self.n,)).copy()
 
     @property
     def D(self):

@@ -173,6 +173,82 @@ __global__ void order_by_iters_kernel(const int *__restrict__ iters, const int *
     for (int b = threadIdx.x; b < n; b += blockDim.x) order[atomicAdd(&base[bucket(iters[b])], 1)] = b;
 }
 
+// Infeasibility certificates of the last solve (OSQP check_termination + store_solution: delta_y projected onto the polar of
+// the recession cone of [l, u], un-scaled with E and normalised to unit infinity norm; delta_x un-scaled with D likewise).
+// The ADMM kernels leave delta_y / delta_x of the terminating iteration in the handle's scratch arrays (compact rows /
+// positions, scaled space); this kernel expands them into the caller's row / variable order.  One CTA per QP.
+__global__ void certificate_kernel(int m, int n, int mu, int np, const int *__restrict__ used_rows, const int *__restrict__ pos_var,
+                                   const int *__restrict__ status, const int *__restrict__ iters, const int *__restrict__ empty_rows, int n_empty,
+                                   const double *__restrict__ l, const double *__restrict__ u,
+                                   const double *__restrict__ Eg, const double *__restrict__ Dg, const double *__restrict__ dyg,
+                                   const double *__restrict__ dxg, int scaled_termination, double *__restrict__ prim, double *__restrict__ dual) {
+    __shared__ double red[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int st = status[b];
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    auto block_max = [&](double v) {
+        for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        double r = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) r = fmax(r, red[k]);
+        return r;
+    };
+    if (prim) {
+        double *out = prim + (size_t)b * m;
+        const bool has = st == -3 || st == 3;
+        for (int i = tid; i < m; i += blockDim.x) out[i] = has ? 0.0 : qnan; // rows without entries never leave y = 0
+        __syncthreads();
+        if (has && iters[b] == 0) {
+            // infeasible before the first iteration: a row of A without entries whose bounds exclude 0 (0 = A_r x is not in
+            // [l_r, u_r]); the unit vector of that row, signed towards the violated side, is the certificate
+            for (int e = tid; e < n_empty; e += blockDim.x) {
+                const int r = empty_rows[e];
+                if (l[(size_t)b * m + r] > 0.0) out[r] = -1.0;
+                else if (u[(size_t)b * m + r] < 0.0) out[r] = 1.0;
+            }
+        } else if (has) {
+            double nrm = 0.0;
+            for (int i = tid; i < mu; i += blockDim.x) {
+                const int orig = used_rows[i];
+                const double e = Eg[(size_t)b * mu + i];
+                const double lo = fmax(l[(size_t)b * m + orig], -kInfty) * e, hi = fmin(u[(size_t)b * m + orig], kInfty) * e;
+                double d = dyg[(size_t)b * mu + i];
+                if (hi > kInfty * kMinScaling) d = lo < -kInfty * kMinScaling ? 0.0 : fmin(d, 0.0);
+                else if (lo < -kInfty * kMinScaling) d = fmax(d, 0.0);
+                if (!scaled_termination) d *= e;
+                out[orig] = d;
+                nrm = fmax(nrm, fabs(d));
+            }
+            nrm = block_max(nrm);
+            const double inv = 1.0 / nrm;
+            for (int i = tid; i < mu; i += blockDim.x) out[used_rows[i]] *= inv;
+        }
+    }
+    if (dual) {
+        double *out = dual + (size_t)b * n;
+        const bool has = (st == -4 || st == 4) && dxg != nullptr;
+        for (int j = tid; j < n; j += blockDim.x) out[j] = qnan;
+        __syncthreads();
+        if (has) {
+            double nrm = 0.0;
+            for (int p = tid; p < np; p += blockDim.x) {
+                const int var = pos_var[p];
+                if (var < 0) continue;
+                double d = dxg[(size_t)b * np + p];
+                if (!scaled_termination) d *= Dg[(size_t)b * np + p];
+                out[var] = d;
+                nrm = fmax(nrm, fabs(d));
+            }
+            nrm = block_max(nrm);
+            const double inv = 1.0 / nrm;
+            for (int p = tid; p < np; p += blockDim.x)
+                if (pos_var[p] >= 0) out[pos_var[p]] *= inv;
+        }
+    }
+}
+
 __global__ void peak_smem_kernel(double *out, int iters) {
     extern __shared__ __align__(16) double buf[];
     const int words = 4096; // 32 KB of doubles per CTA
@@ -1013,6 +1089,44 @@ int gomp_batch_get_info(gomp_batch *h, double *pri_res, double *dua_res, double 
     if ((rc = copy_out(h, rho, h->d_rho.p, B * sizeof(double)))) return rc;
     if ((rc = copy_out(h, obj_val, h->d_obj.p, B * sizeof(double)))) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GOMP_OK;
+}
+
+int gomp_batch_get_certificates(gomp_batch *h, double *prim_inf_cert, double *dual_inf_cert) {
+    if (!h) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
+    if (h->launches == 0) return fail(GOMP_ERR_INVALID_ARGUMENT, "no solve has been run on this handle");
+    if (!prim_inf_cert && !dual_inf_cert) return GOMP_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t B = (size_t)h->batch;
+    const gomp::Symbolic &s = h->sym;
+    // device outputs are written in place; host outputs go through a staging buffer on the handle's device
+    double *dp = nullptr, *dd = nullptr;
+    DevArray<double> tp, td;
+    if (prim_inf_cert) {
+        if (is_device_pointer(prim_inf_cert)) dp = prim_inf_cert;
+        else {
+            CUDA_TRY(tp.alloc(B * (size_t)s.m));
+            dp = tp.p;
+        }
+    }
+    if (dual_inf_cert) {
+        if (is_device_pointer(dual_inf_cert)) dd = dual_inf_cert;
+        else {
+            CUDA_TRY(td.alloc(B * (size_t)s.n));
+            dd = td.p;
+        }
+    }
+    certificate_kernel<<<(unsigned)B, 256, 0, h->stream>>>((int)s.m, (int)s.n, s.m_used, s.n_pad, h->d_used_rows.p, h->d_pos_var.p, h->d_status.p,
+                                                          h->d_iters.p, h->d_empty_rows.p, (int)s.empty_rows.size(), h->l_src, h->u_src, h->d_E.p, h->d_D.p, h->d_dy.p, h->has_q ? h->d_dx.p : nullptr,
+                                                          h->st.scaled_termination, dp, dd);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && tp.p) e = cudaMemcpyAsync(prim_inf_cert, tp.p, B * (size_t)s.m * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && td.p) e = cudaMemcpyAsync(dual_inf_cert, td.p, B * (size_t)s.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    tp.release();
+    td.release();
+    if (e != cudaSuccess) return fail(GOMP_ERR_CUDA, std::string("certificates: ") + cudaGetErrorString(e));
+    h->launches += 1;
     return GOMP_OK;
 }
 

@@ -33,7 +33,7 @@ public:
     };
 
     GOMPBatchSolver(const gomp_problem_config &cfg, long long first_id, long long count, const gomp_settings *settings = nullptr)
-        : cfg_(cfg), count_(count) {
+        : cfg_(cfg), first_id_(first_id), count_(count) {
         int64_t nnzP = 0;
         check(gomp_problem_dims(&cfg_, &n_, &m_, &nnzA_, &nnzP), "gomp_problem_dims");
         std::vector<int64_t> Ap((size_t)n_ + 1), Ai((size_t)nnzA_), Pp((size_t)n_ + 1), Pi((size_t)nnzP), order((size_t)n_);
@@ -82,6 +82,17 @@ public:
         r.qp_exit_code.assign(B, kUnknown);
         r.rounds.assign(B, 0);
         std::vector<int32_t> running(B, 1), code(B), ok(B);
+        if (ran_) {
+            // A second run starts over like the first: the rounds rewrote A_val / l / u in place and left the iterates, duals
+            // and rho of the last round on the device, whereas the reference builds a fresh QPSolver per run
+            // (src/gomp-solver.h:61-65).  Regenerate the initial linearisation and cold-start the handle.
+            std::vector<double> A_val((size_t)(count_ * nnzA_)), l((size_t)(count_ * m_)), u((size_t)(count_ * m_));
+            check(gomp_problem_generate(&cfg_, first_id_, count_, A_val.data(), l.data(), u.data(), nullptr, nullptr, 0), "gomp_problem_generate");
+            check(gomp_batch_setup(solver_, A_val.data(), l.data(), u.data(), nullptr), "gomp_batch_setup");
+            check(gomp_batch_sync(solver_), "gomp_batch_sync"); // the host arrays above go out of scope
+            check(gomp_batch_device_views(solver_, &dA_, &dl_, &du_, &dx_, &stream_), "gomp_batch_device_views");
+        }
+        ran_ = true;
         check(gomp_batch_warm_start_x(solver_, x0_.data()), "gomp_batch_warm_start_x");
         check(gomp_batch_set_active(solver_, nullptr), "gomp_batch_set_active");
         for (int round = 0; round < max_rounds; ++round) {
@@ -118,7 +129,8 @@ private:
         if (rc != 0) throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + gomp_last_error_string());
     }
     gomp_problem_config cfg_;
-    long long count_;
+    long long first_id_, count_;
+    bool ran_ = false;
     int64_t n_ = 0, m_ = 0, nnzA_ = 0;
     gomp_batch *solver_ = nullptr;
     gomp_device_scene *scene_ = nullptr;

@@ -18,7 +18,7 @@ EXIT_NAMES = ["kOptimal", "kPrimalInfeasible", "kDualInfeasible", "kOptimalInacc
               "kDualInfeasibleInaccurate", "kMaxIterations", "kInterrupted", "kTimeLimitReached", "kNonConvex", "kUnknown"]
 
 EXPORTS = ["gomp_settings_default", "gomp_batch_create", "gomp_batch_setup", "gomp_batch_warm_start_x", "gomp_batch_solve",
-           "gomp_batch_update", "gomp_batch_set_active", "gomp_batch_get", "gomp_batch_get_async", "gomp_batch_get_info", "gomp_batch_info", "gomp_batch_sync",
+           "gomp_batch_update", "gomp_batch_set_active", "gomp_batch_get", "gomp_batch_get_async", "gomp_batch_get_info", "gomp_batch_get_certificates", "gomp_batch_info", "gomp_batch_sync",
            "gomp_batch_destroy", "gomp_batch_device_views", "gomp_device_malloc", "gomp_device_free", "gomp_device_memcpy",
            "gomp_measure_peaks", "gomp_last_error_string", "gomp_device_count", "gomp_version",
            "gomp_mg_create", "gomp_mg_setup", "gomp_mg_warm_start_x", "gomp_mg_update", "gomp_mg_solve", "gomp_mg_get", "gomp_mg_shard",
@@ -218,6 +218,15 @@ class BatchQPSolver:
         rho = np.empty(self.batch)
         _check(lib().gomp_batch_get_info(self.h, C.c_void_p(pri.ctypes.data), C.c_void_p(dua.ctypes.data), C.c_void_p(rho.ctypes.data), None))
         return dict(pri_res=pri, dua_res=dua, rho=rho)
+
+    def certificates(self, primal=True, dual=False):
+        """Infeasibility certificates of the last solve: (prim_inf_cert [batch, m] | None, dual_inf_cert [batch, n] | None);
+        NaN rows for problems whose status is not (inaccurately) primal / dual infeasible."""
+        pc = np.empty((self.batch, self.m)) if primal else None
+        dc = np.empty((self.batch, self.n)) if dual else None
+        _check(lib().gomp_batch_get_certificates(self.h, None if pc is None else C.c_void_p(pc.ctypes.data),
+                                                 None if dc is None else C.c_void_p(dc.ctypes.data)))
+        return pc, dc
 
     def info(self):
         inf = Info()

@@ -19,7 +19,10 @@ K_OPTIMAL, K_UNKNOWN = 0, 10
 
 
 class BatchSQP:
-    def __init__(self, pattern, first_id, count, settings=None, device=None):
+    def __init__(self, pattern, first_id, count, settings=None, device=None, warm_start=None):
+        """warm_start [count, n] (optional): the trajectory each problem is warm-started from AND linearised around, as
+        GOMPSolver::run(start, goal, waypoints, warm_start) does (reference src/gomp-solver.h:57-65, initConstraints);
+        default: the straight line of gomp-solver.h:105-116."""
         import torch
         self.torch = torch
         self.pattern, self.first_id, self.count = pattern, first_id, count
@@ -27,16 +30,27 @@ class BatchSQP:
         st = settings if settings is not None else _solver.default_settings()
         st.borrow_inputs = 1
         st.stream = self.stream.cuda_stream
-        host = _problem.generate(pattern, first_id, count)
+        if warm_start is None:
+            host = _problem.generate(pattern, first_id, count)
+        else:
+            warm_start = np.ascontiguousarray(warm_start, dtype=np.float64)
+            assert warm_start.shape == (count, pattern.n)
+            host = _problem.relinearize(pattern, first_id, warm_start)
+            host["x0"] = warm_start
         self.host = host
         self.dev = {k: torch.from_numpy(host[k]).cuda() for k in ("A_val", "l", "u", "x0")}
         self.solver = _solver.BatchQPSolver(pattern.n, pattern.m, pattern.P_colptr, pattern.P_rowidx, pattern.P_val,
                                             pattern.A_colptr, pattern.A_rowidx, self.dev["A_val"], self.dev["l"], self.dev["u"],
                                             batch=count, settings=st, var_order=pattern.var_order, block_size=pattern.block_size)
         self.scene = _problem.DeviceScene(pattern, first_id, count)
-        self.x = torch.empty((count, pattern.n), dtype=torch.float64, device="cuda")
-        self.ok = torch.empty(count, dtype=torch.int32, device="cuda")
-        self.active = torch.ones(count, dtype=torch.int32, device="cuda")
+        # every buffer the solver borrows is created and written on the solver's stream (the stream is non-blocking: nothing
+        # orders it against torch's default stream)
+        with torch.cuda.stream(self.stream):
+            self.x = torch.empty((count, pattern.n), dtype=torch.float64, device="cuda")
+            self.ok = torch.empty(count, dtype=torch.int32, device="cuda")
+            self.active = torch.ones(count, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()  # the uploads above ran on the default stream
+        self._ran = False
 
     def run(self, max_rounds=MAX_ITERATIONS):
         """Returns dict(exit_code [count] (kOptimal / kUnknown as GOMPSolver::run reports them), qp_exit_code (the last
@@ -44,13 +58,22 @@ class BatchSQP:
         torch = self.torch
         B = self.count
         s = self.solver
+        if self._ran:
+            # a second run starts over like the first one: the rounds rewrote A_val / l / u in place and left iterates, duals
+            # and rho of the last round on the device -- the reference builds a fresh QPSolver per run (gomp-solver.h:61-65)
+            with torch.cuda.stream(self.stream):
+                for k in ("A_val", "l", "u"):
+                    self.dev[k].copy_(torch.from_numpy(self.host[k]), non_blocking=False)
+            s.setup(self.dev["A_val"], self.dev["l"], self.dev["u"])
+        self._ran = True
         s.set_warm_start(self.dev["x0"])
         running = np.ones(B, dtype=bool)
         code = np.full(B, K_UNKNOWN, dtype=np.int32)
         qp_code = np.full(B, K_UNKNOWN, dtype=np.int32)
         rounds = np.zeros(B, dtype=np.int32)
         total = 0
-        self.active.fill_(1)
+        with torch.cuda.stream(self.stream):
+            self.active.fill_(1)
         s.set_active(self.active)
         sc = self.stream.cuda_stream
         for rnd in range(max_rounds):
@@ -85,8 +108,50 @@ class BatchSQP:
 SEGMENTS = 10  # reference src/gomp-solver.h:11
 
 
+def shortest_horizon_chained(cfg, first_id, count, max_rounds=MAX_ITERATIONS, settings_factory=None):
+    """GOMPSolver::run(start, goal) with the reference's OWN semantics (src/gomp-solver.h:38-55) for a batch: the horizons
+    W*i/SEGMENTS, i = SEGMENTS..1, are solved one after the other (one batch over all problems per horizon), and every horizon
+    is warm-started from -- and linearised around -- the slices of the last kOptimal trajectory exactly as :43-44 takes them:
+    the first w*N entries, then the w*N entries that follow them (for a shrinking horizon those are NOT the velocities of the
+    previous solution but the tail of its positions and the head of its velocities; kept verbatim, as the facade's
+    GOMPSolver<N>::run does).  A horizon's run reports kOptimal or kUnknown only (:66-90), so no horizon is skipped (:46-48).
+
+    Returns the dict of `shortest_horizon` plus codes_per_horizon [H, count]."""
+    import copy
+    W, N = cfg.waypoints, cfg.n_dim
+    pat_full = _problem.Pattern(cfg)
+    last = list(_problem.generate(pat_full, first_id, count)["x0"])   # calcWarmStart: [linspace | 0] at the full horizon
+    code = np.full(count, K_UNKNOWN, dtype=np.int32)
+    chosen = np.zeros(count, dtype=np.int32)
+    horizons, codes, total = [], [], 0
+    for i in range(SEGMENTS, 0, -1):
+        w = W * i // SEGMENTS
+        if w < 4:
+            break                                                      # (the reference asserts waypoints >= 4)
+        c = copy.copy(cfg)
+        c.waypoints = w
+        pat = _problem.Pattern(c)
+        warm = np.stack([np.concatenate([v[:w * N], v[w * N:2 * w * N]]) for v in last])
+        drv = BatchSQP(pat, first_id, count, settings=settings_factory() if settings_factory else None, warm_start=warm)
+        out = drv.run(max_rounds=max_rounds)
+        x = out["x"].cpu().numpy()
+        drv.close()
+        total += out["total_qp_solves"]
+        horizons.append(w)
+        codes.append(out["exit_code"].copy())
+        for b in np.flatnonzero(out["exit_code"] == K_OPTIMAL):
+            code[b], chosen[b], last[b] = K_OPTIMAL, w, x[b].copy()
+    xs = []
+    for b in range(count):
+        v = last[b].copy()
+        v[v.size // 2:] /= cfg.time_step                               # :52 velocities per second
+        xs.append(v)
+    return dict(exit_code=code, waypoints=chosen, x=xs, horizons=horizons, qp_solves=total, codes_per_horizon=np.array(codes))
+
+
 def shortest_horizon(cfg, first_id, count, max_rounds=MAX_ITERATIONS, settings_factory=None):
-    """GOMPSolver::run(start, goal) -- the time-shrink outer loop of reference src/gomp-solver.h:38-55 -- for a batch.
+    """GOMPSolver::run(start, goal) -- the time-shrink outer loop of reference src/gomp-solver.h:38-55 -- for a batch, with every
+    horizon independent of the others (see `shortest_horizon_chained` for the reference's chained warm starts).
 
     The reference solves the horizons W*i/SEGMENTS, i = SEGMENTS..1, one after the other, keeps the last kOptimal
     trajectory and stops at the first horizon whose QP fails.  Given a warm start the horizons are independent, so

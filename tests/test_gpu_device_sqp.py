@@ -143,7 +143,8 @@ def test_cpp_batch_solver_matches_python_driver():
     exe = os.path.join(pkg_dir, "build", "batch-sqp-example")
     subprocess.check_call(["make", "-C", pkg_dir, "example"], stdout=subprocess.DEVNULL)
     B, first, max_rounds = 48, 100, 10
-    out = subprocess.run([exe, str(B), str(first), str(max_rounds)], capture_output=True, text=True, check=True).stdout.splitlines()
+    out = subprocess.run([exe, str(B), str(first), str(max_rounds), "rerun"], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[2].strip() == "rerun_equal 1"   # GOMPBatchSolver::run is re-entrant
     pairs = [tuple(int(v) for v in tok.split(":")) for tok in out[1].split()[1:]]
     drv = pkg.sqp.BatchSQP(P.Pattern(P.default_config()), first, B)
     ref = drv.run(max_rounds=max_rounds)
@@ -176,3 +177,67 @@ def test_shortest_horizon_batch():
         assert x.shape == (pat.n,)
         x[pat.n // 2:] *= cfg.time_step   # back to per-step velocities for the check
         assert P.check(pat, 300 + b, x[None, :])[0]
+
+
+def test_chained_time_shrink_matches_reference_loop():
+    """GOMPSolver::run(start, goal) with the reference's chained warm starts (src/gomp-solver.h:38-55, the slicing of :43-44
+    included): the batched driver against the same loop run problem by problem on the CPU (oracle QP solver + host
+    withObstacles / isSolutionOK) -- per-horizon exit codes, the horizon kept, and the returned trajectory."""
+    import copy
+    pkg, O = package(), oracle()
+    P = pkg.problem
+    cfg = P.default_config(waypoints=40)
+    first, B, max_rounds = 500, 10, 8
+    N, W = cfg.n_dim, cfg.waypoints
+    out = pkg.sqp.shortest_horizon_chained(cfg, first, B, max_rounds=max_rounds)
+    assert out["horizons"] == [40, 36, 32, 28, 24, 20, 16, 12, 8, 4]
+    pats = {}
+    for w in out["horizons"]:
+        c = copy.copy(cfg)
+        c.waypoints = w
+        pats[w] = P.Pattern(c)
+    full = P.generate(pats[W], first, B)
+    for b in range(B):
+        last, code, kept = full["x0"][b].copy(), 10, 0                       # :39-40
+        for k, w in enumerate(out["horizons"]):                              # :41-42
+            pat = pats[w]
+            warm = np.concatenate([last[:w * N], last[w * N:2 * w * N]])     # :43-44
+            d = P.relinearize(pat, first + b, warm[None, :])                 # :58 initConstraints(..., warm_start, waypoints)
+            ref = O.Solver(pat.P_scipy(), pat.A_scipy(d["A_val"][0]), d["l"][0], d["u"][0])
+            ref.warm_start_x(warm)                                           # :65
+            hcode, sol = 10, warm
+            for rnd in range(max_rounds):                                    # :70
+                ref.solve()
+                sol = ref.x
+                if ref.exit_code != 0:                                       # :72-76
+                    break
+                if P.check(pat, first + b, sol[None, :])[0]:                 # :77-81
+                    hcode = 0
+                    break
+                upd = P.relinearize(pat, first + b, sol[None, :])            # :83-87
+                ref.update(upd["A_val"][0], upd["l"][0], upd["u"][0])
+            assert out["codes_per_horizon"][k][b] == hcode, (b, w, out["codes_per_horizon"][k][b], hcode)
+            if hcode == 0:                                                   # :48-51
+                code, kept, last = 0, w, sol.copy()
+        assert out["exit_code"][b] == code and out["waypoints"][b] == kept
+        want = last.copy()
+        want[want.size // 2:] /= cfg.time_step                               # :52
+        assert out["x"][b].shape == want.shape
+        assert np.abs(out["x"][b] - want).max() <= 1e-6 * max(1.0, np.abs(want).max())
+    assert (out["exit_code"] == 0).any() and len(set(out["waypoints"].tolist())) > 1
+
+
+def test_batch_sqp_run_is_reentrant():
+    """a second run() used to start from the last round's linearisation with stale duals and rho; it now
+    starts over (fresh QPSolver per run in the reference, src/gomp-solver.h:61-65) and reproduces the first run."""
+    pkg = package()
+    P = pkg.problem
+    drv = pkg.sqp.BatchSQP(P.Pattern(P.default_config()), 60, 24)
+    a = drv.run(max_rounds=6)
+    xa = a["x"].cpu().numpy().copy()
+    b = drv.run(max_rounds=6)
+    assert (a["rounds"] > 1).any()
+    np.testing.assert_array_equal(a["exit_code"], b["exit_code"])
+    np.testing.assert_array_equal(a["rounds"], b["rounds"])
+    np.testing.assert_array_equal(np.nan_to_num(xa), np.nan_to_num(b["x"].cpu().numpy()))
+    drv.close()

@@ -215,3 +215,37 @@ def test_two_slot_backend_shapes(kw):
     got = s.solve(want_y=True)
     s.close()
     compare(got, oracle_batch(O, pat, d))
+
+
+def test_reference_example_shape_n6_w802():
+    """BASELINE.json configs[0]: the shape of the reference's only end-to-end configuration (examples/solver-example.cpp:12-16:
+    N = 6 joints, 802 waypoints, two collision balls, no obstacle lines -> n = 9 624, m = 33 660, nnz(A) = 48 060) on the streamed
+    back end against the oracle.  The UR5e kinematics of the example are not vendored; the synthetic chain truncated to six
+    joints stands in."""
+    pkg, O = package(), oracle()
+    P = pkg.problem
+    pat = P.Pattern(P.default_config(n_dim=6, waypoints=802, n_balls=2, n_obstacles=0))
+    assert (pat.n, pat.m, pat.nnzA) == (9624, 33660, 48060)
+    d = P.generate(pat, 0, 3)
+    s = make_solver(pkg, pat, d)
+    assert s.info()["linsys"] == GLOBAL
+    s.set_warm_start(d["x0"])
+    got = s.solve(want_y=True)
+    compare(got, oracle_batch(O, pat, d))
+    # one SQP round on top: withObstacles(x) -> update -> solve (reference src/gomp-solver.h:83-87)
+    ok = got["exit_code"] == 0
+    x = np.where(ok[:, None], got["x"], d["x0"])
+    upd = P.relinearize(pat, 0, x)
+    s.update(upd["A_val"], upd["l"], upd["u"])
+    got2 = s.solve()
+    s.close()
+    Ps = pat.P_scipy()
+    for b in range(3):
+        ref = O.Solver(Ps, pat.A_scipy(d["A_val"][b]), d["l"][b], d["u"][b])
+        ref.warm_start_x(d["x0"][b])
+        ref.solve()
+        ref.update(upd["A_val"][b], upd["l"][b], upd["u"][b])
+        ref.solve()
+        assert got2["exit_code"][b] == ref.exit_code and got2["iters"][b] == ref.iter
+        if ref.exit_code == 0:
+            assert np.abs(got2["x"][b] - ref.x).max() < REL_TOL * np.abs(ref.x).max()

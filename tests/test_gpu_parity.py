@@ -242,6 +242,10 @@ def test_infeasible_and_unbounded():
     ref.solve()
     assert r["exit_code"][0] == ref.exit_code == 1 and r["iters"][0] == ref.iter
     assert np.isnan(r["x"]).all()
+    # the certificate osqp-cpp would hand out (primal_infeasibility_certificate): unit infinity norm, A'v = 0, support < 0
+    pc, dc = s.certificates(primal=True, dual=True)
+    np.testing.assert_allclose(pc[0], ref.prim_inf_cert, rtol=1e-9, atol=1e-12)
+    assert np.isnan(dc).all() and abs(np.abs(pc[0]).max() - 1.0) < 1e-12
     s.close()
 
     P0 = sp.csc_matrix((1, 1))
@@ -252,6 +256,9 @@ def test_infeasible_and_unbounded():
     ref = O.Solver(P0, A1, np.array([0.0]), np.array([1e30]), q=np.array([-1.0]))
     ref.solve()
     assert r["exit_code"][0] == ref.exit_code == 2 and r["iters"][0] == ref.iter
+    pc, dc = s.certificates(primal=True, dual=True)
+    np.testing.assert_allclose(dc[0], ref.dual_inf_cert, rtol=1e-9, atol=1e-12)
+    assert np.isnan(pc).all()
     s.close()
 
     A2 = sp.csc_matrix(np.array([[1.0, 0.0], [0.0, 0.0]]))  # second row empty, bounds [1, 2] exclude 0
@@ -259,7 +266,38 @@ def test_infeasible_and_unbounded():
                         np.array([[-1.0, 1.0]]), np.array([[1.0, 2.0]]))
     r = s.solve()
     assert r["exit_code"][0] == 1
+    pc, _ = s.certificates()
+    np.testing.assert_array_equal(pc[0], [0.0, -1.0])   # the empty row's unit vector, signed towards the violated bound
     s.close()
+
+
+def test_primal_infeasibility_certificates_on_gomp_batch(env):
+    """the certificates through the API on the headline shape.  The batch holds primal infeasible QPs
+    (~2 % of the workload): their certificate equals the oracle's delta_y and certifies infeasibility of the QP the caller
+    passed (A'v ~ 0, u'v+ + l'v- < 0); every other problem reports NaN."""
+    pkg, O, pat = env
+    B = 160
+    d = pkg.problem.generate(pat, 0, B)
+    s = make_solver(pkg, pat, d)
+    s.set_warm_start(d["x0"])
+    got = s.solve()
+    pc, _ = s.certificates()
+    s.close()
+    inf = np.isin(got["exit_code"], [1, 4])
+    assert inf.any() and np.isnan(pc[~inf]).all() and not np.isnan(pc[inf]).any()
+    Ps = pat.P_scipy()
+    for b in np.flatnonzero(inf):
+        A = pat.A_scipy(d["A_val"][b])
+        ref = O.Solver(Ps, A, d["l"][b], d["u"][b])
+        ref.warm_start_x(d["x0"][b])
+        ref.solve()
+        assert ref.exit_code == got["exit_code"][b]
+        v = pc[b]
+        np.testing.assert_allclose(v, ref.prim_inf_cert, rtol=1e-6, atol=1e-9)
+        assert abs(np.abs(v).max() - 1.0) < 1e-12
+        lo, hi = np.maximum(d["l"][b], -1e30), np.minimum(d["u"][b], 1e30)
+        support = hi @ np.maximum(v, 0.0) + lo @ np.minimum(v, 0.0)
+        assert support < 0 and np.abs(A.T @ v).max() < 1e-3 * abs(support) + 1e-3
 
 
 def test_update_rejects_bad_bounds(env):

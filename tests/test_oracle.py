@@ -114,3 +114,24 @@ def test_kkt_ordering_is_a_permutation():
     P = sp.identity(12, format="csc")
     perm = O.kkt_ordering(12, 20, P.indptr, P.indices, A.indptr, A.indices)
     assert sorted(perm.tolist()) == list(range(32))
+
+
+def test_infeasibility_certificates_are_normalised():
+    """OSQP store_solution: delta_y / delta_x of an infeasible problem are handed out with unit infinity norm (what osqp-cpp's
+    primal_infeasibility_certificate / dual_infeasibility_certificate expose) and certify infeasibility."""
+    import scipy.sparse as sp
+    O = oracle()
+    P = sp.csc_matrix(np.eye(2))
+    A = sp.csc_matrix(np.array([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0]]))
+    l, u = np.array([1.0, -5.0, -1.0]), np.array([2.0, 0.0, 1.0])
+    s = O.Solver(P, A, l, u)
+    s.solve()
+    assert s.exit_code == 1
+    v = s.prim_inf_cert
+    assert abs(np.abs(v).max() - 1.0) < 1e-12 and np.abs(A.T @ v).max() < 1e-6
+    assert u @ np.maximum(v, 0) + l @ np.minimum(v, 0) < 0
+    s = O.Solver(sp.csc_matrix((1, 1)), sp.csc_matrix(np.array([[1.0]])), np.array([0.0]), np.array([1e30]), q=np.array([-1.0]))
+    s.solve()
+    assert s.exit_code == 2
+    w = s.dual_inf_cert
+    assert abs(np.abs(w).max() - 1.0) < 1e-12 and -1.0 * w[0] < 0
