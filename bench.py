@@ -97,6 +97,7 @@ class ClockSampler:
 # start + solve.  The timed region ends with the drain of the last batches (their max_iter QPs take 70 ms each), so
 # few steps under-report the steady state: 32 steps 197 k, 128 steps 213 k on one build; 64 -> 233 k, 256 -> 241 k now.
 PIPE = int(os.environ.get("GOMP_BENCH_PIPE", "12"))
+GATHER = os.environ.get("GOMP_BENCH_GATHER", "1") != "0"  # A/B switch: the per-step NCCL gather of the multi-GPU runs
 
 
 def workload(pkg):
@@ -428,6 +429,11 @@ def run_gpu(args):
     if world > 1:
         # NCCL prints its version banner with printf when the communicator is created: keep it off stdout, which carries
         # the one JSON line (fd 1 points at stderr until the communicator exists)
+        # The solver's persistent CTAs own every SM's register file, so a collective's kernel can only start on an SM a solver CTA
+        # has just left, and holds it while it runs: keep NCCL's point-to-point traffic (the gather is send / recv) on few
+        # channels = few CTAs.  161 MB per step into rank 0 at 8 GPUs needs ~10 GB/s, a fraction of one NVLink channel pair.
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "2")
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "1")
         sys.stdout.flush()
         saved = os.dup(1)
         os.dup2(2, 1)
@@ -508,7 +514,7 @@ def run_gpu(args):
             st_.wait_event(ev0)
         for k in range(nsteps):
             step_resident(k)
-            if world > 1:
+            if world > 1 and GATHER:
                 gather_step(k)
         for st_ in streams:
             e = torch.cuda.Event()
@@ -529,7 +535,7 @@ def run_gpu(args):
     clocks = sampler.stop()
     total_ms = ev0.elapsed_time(ev1)
     gathered_ok = None
-    if world > 1 and rank == 0:
+    if world > 1 and rank == 0 and GATHER:
         # the last step's gathered block of every rank against this rank's own results (all ranks solve their own ids; rank 0's
         # block must be its own x bit for bit, the others must carry valid exit codes)
         j = (args.steps - 1) % PIPE
@@ -642,7 +648,15 @@ def run_gpu(args):
         tj = json.load(open(tpath))
         traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * B / tj["qps_per_launch"]
         traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum per launch, " + tj["capture"]
-        ncu = {k: tj[k] for k in ("lsu_wavefront_pct", "issue_pct", "warp_instructions_per_qp", "smem_wavefronts_per_qp") if k in tj}
+        ncu = {k: tj[k] for k in ("warp_instructions_per_qp", "smem_wavefronts_per_qp") if k in tj}
+        if "smem_wavefronts" in tj and "warp_instructions" in tj:
+            # the capture's per-launch counts spread over this run's measured step time at the measured SM clock: share of the
+            # LSU's shared-memory wavefront slots (1 per SM and cycle) and of the warp-issue slots (1 per SM sub-partition and cycle)
+            cycles = step_s * 1e6 * float(clocks.get("sm_mhz") or 1965.0)
+            scale = B / tj["qps_per_launch"]
+            ncu["lsu_wavefront_pct"] = 100.0 * tj["smem_wavefronts"] * scale / (info["num_sms"] * cycles)
+            ncu["issue_pct"] = 100.0 * tj["warp_instructions"] * scale / (4 * info["num_sms"] * cycles)
+            ncu["utilisation_source"] = "counts of " + tj["report"] + " / (slots in this run's ms_per_step at clocks.sm_mhz)"
     roofline = {"bound": "smem", "achieved": smem_bytes / step_s / 1e9, "peak": smem_peak, "unit": "GB/s",
                 "frac": smem_bytes / step_s / 1e9 / smem_peak, "frac_solo": smem_bytes / ksec / 1e9 / smem_peak,
                 "algorithmic_smem_bytes": float(smem_bytes), "traffic": traffic, "traffic_source": traffic_src,

@@ -62,7 +62,7 @@ extern "C" {
                                          through shared memory with TMA (long horizons: H = 400, the reference example's 802) */
 #define GOMP_LINSYS_PCG 3             /* reserved: not built (an inexact solve would change OSQP's iteration counts);
                                          gomp_batch_create returns GOMP_ERR_UNSUPPORTED */
-#define GOMP_LINSYS_BLOCKTRI_TMEM 4   /* same factorisation, TWO QPs resident per SM: one 576-thread CTA with two independent
+#define GOMP_LINSYS_BLOCKTRI_TMEM 4   /* same factorisation, TWO QPs resident per SM: one 512-thread CTA with two independent
                                          slots, the inverted pivot blocks of both QPs kept in tensor memory (tcgen05.st / ld,
                                          lane-private), the block factorisation inside the substitution warps.  Block size
                                          14 or 12 with the uniform 2-wide off-diagonal pattern, 4..63 stages; AUTO picks it
