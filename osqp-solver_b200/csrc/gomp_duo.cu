@@ -941,21 +941,6 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                 // ---------------- residuals and the norms OSQP's tolerances need (update_info)
                 const size_t bmu = (size_t)b * mu, bnp = (size_t)b * np;
                 const double cscale = lds_f64(aCtl + 16u), cinv = lds_f64(aCtl + 24u);
-                // Everything this check reads from global memory is requested here, in one batch of independent loads: the check
-                // executes 2 % of a QP's instructions, and what it used to cost (31 k cycles) were ~20 exposed L2 round trips --
-                // one per P entry and per scaling factor, each issued only after the previous one had been consumed.
-                constexpr int PFW = 4;
-                const uint32_t ppad = ((uint32_t)(np * 8) << 16) | (uint32_t)(S.nnzPu * 8);
-                uint32_t pfe[CPT][PFW];
-                double dgv[CPT], egv[RPT];
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-#pragma unroll
-                    for (int q = 0; q < PFW; ++q) pfe[c][q] = q < X.plen[c] ? X.pf_ell[X.pbase[c] + q * kDuoOwners + oid] : ppad;
-                    dgv[c] = pos8[c] >= 0 ? B.Dg[bnp + (pos8[c] >> 3)] : 1.0;
-                }
-#pragma unroll
-                for (int j = 0; j < RPT; ++j) egv[j] = oid + j * kDuoOwners < mu ? B.Eg[bmu + oid + j * kDuoOwners] : 1.0;
                 COLS_LOOP(c, p8) sts_f64(aR + (uint32_t)p8, x[c]);
                 ROWS_LOOP(j, i) sts_f64(aW + (uint32_t)i * 8u, y[j]);
                 w_dirty = true;
@@ -970,7 +955,7 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                     ROWS_LOOP(j, i) {
                         const double ax = axv[j];
                         const double pr = ax - z[j];
-                        const double einv = 1.0 / egv[j];
+                        const double einv = 1.0 / B.Eg[bmu + i];
                         na[0] = fmax(na[0], fabs(einv * pr));
                         na[1] = fmax(na[1], fabs(pr));
                         na[2] = fmax(na[2], fabs(einv * z[j]));
@@ -989,12 +974,11 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                     DUO_DOT(false, CPT, atyv, aA, aW, aColMine, cpad);
                     COLS_LOOP(c, p8) {
                         double px = 0.0;
-#pragma unroll
-                        for (int q = 0; q < PFW; ++q) px = fma(lds_f64(aP + LO16(pfe[c][q])), lds_f64(aR + HI16(pfe[c][q])), px); // (surplus entries: 0 * 0)
+                        PF_ENTRIES(c, e) px = fma(lds_f64(aP + LO16(e)), lds_f64(aR + HI16(e)), px);
                         const double aty = atyv[c];
                         const double qq = hasq ? B.qs[bnp + (p8 >> 3)] : 0.0;
                         const double du = qq + px + aty;
-                        const double dinv = 1.0 / dgv[c];
+                        const double dinv = 1.0 / B.Dg[bnp + (p8 >> 3)];
                         nb[0] = fmax(nb[0], fabs(dinv * du));
                         nb[1] = fmax(nb[1], fabs(du));
                         nb[2] = fmax(nb[2], fabs(dinv * px));
@@ -1058,11 +1042,8 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                     } else {
                         // OSQP is_primal_infeasible on delta_y (projected onto the polar of the recession cone, kept in sW)
                         double nrm[1] = {0.0}, lhs = 0.0;
-                        double dyv[RPT];
-#pragma unroll
-                        for (int j = 0; j < RPT; ++j) dyv[j] = oid + j * kDuoOwners < mu ? B.dyg[bmu + oid + j * kDuoOwners] : 0.0;
                         ROWS_LOOP(j, i) {
-                            double d = dyv[j];
+                            double d = B.dyg[bmu + i];
                             const double l_ = lds_f64(aLo + (uint32_t)i * 8u), u_ = lds_f64(aHi + (uint32_t)i * 8u);
                             if (u_ > kInfty * kMinScaling) {
                                 if (l_ < -kInfty * kMinScaling) d = 0.0;
@@ -1071,7 +1052,7 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                                 d = fmax(d, 0.0);
                             }
                             sts_f64(aW + (uint32_t)i * 8u, d);
-                            nrm[0] = fmax(nrm[0], fabs(uns ? egv[j] * d : d));
+                            nrm[0] = fmax(nrm[0], fabs(uns ? B.Eg[bmu + i] * d : d));
                             lhs += u_ * fmax(d, 0.0) + l_ * fmin(d, 0.0);
                         }
                         duo_max<1>(nrm, sRed, oid, bOwn); // (also orders the sW writes before the gather below)
@@ -1082,7 +1063,7 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
 #pragma unroll
                             for (int c = 0; c < CPT; ++c) accv[c] = 0.0;
                             DUO_DOT(false, CPT, accv, aA, aW, aColMine, cpad);
-                            COLS_LOOP(c, p8) v[0] = fmax(v[0], fabs(uns ? (1.0 / dgv[c]) * accv[c] : accv[c]));
+                            COLS_LOOP(c, p8) v[0] = fmax(v[0], fabs(uns ? (1.0 / B.Dg[bnp + (p8 >> 3)]) * accv[c] : accv[c]));
                             duo_max<1>(v, sRed, oid, bOwn);
                             pic = v[0] < epi * nrm[0];
                         }
