@@ -203,9 +203,8 @@ def strong_scaling(pkg, pat, rank, world, local_rank, torch, dist):
         return None
     chunk = int(os.environ.get("GOMP_BENCH_STRONG_CHUNK", "16384"))
     nh = 4
-    per = (total + world - 1) // world
-    lo, hi = rank * per, min(total, (rank + 1) * per)
-    count = max(0, hi - lo)
+    lo, hi = pkg.sharding.shard_range(total, rank, world)   # contiguous id ranges, sizes differ by at most one
+    count = hi - lo
     chunk = max(1, min(chunk, count))
     nchunks = (count + chunk - 1) // chunk
     N = pat.cfg.n_dim

@@ -19,8 +19,13 @@
  *
  * Conventions: plain pointers and sizes, int return codes (0 = OK), no exceptions, no
  * C++/torch types.  Every data pointer may be a HOST or a DEVICE pointer (detected with
- * cudaPointerGetAttributes); the library copies what it needs during the call, so no
- * caller buffer has to outlive a call (as with osqp-cpp, SURVEY.md 8b "Ownership").
+ * cudaPointerGetAttributes).  Pageable host arrays are copied during the call and need not
+ * outlive it (as with osqp-cpp, SURVEY.md 8b "Ownership"); copies from PINNED host memory are
+ * truly asynchronous on the handle's stream, so a pinned input must stay unchanged until the next
+ * gomp_batch_sync / gomp_batch_get on that handle; device inputs with settings.borrow_inputs are
+ * used in place until the next setup / update.  Host bounds are validated (l <= u) during the
+ * call; device-resident bounds are validated on the device and a violation is reported by the
+ * next gomp_batch_sync / gomp_batch_get (GOMP_ERR_INVALID_ARGUMENT).
  * One handle is not thread-safe; distinct handles are.  All arithmetic is fp64.
  * There is no CPU fallback: without a CUDA device every compute entry point fails.
  */

@@ -249,6 +249,14 @@ __global__ void certificate_kernel(int m, int n, int mu, int np, const int *__re
     }
 }
 
+// l <= u for device-resident bounds (the host path checks on the CPU before copying): one flag per handle, read back with
+// the results.  OSQP refuses such data (validate_data / osqp_update_bounds), the reference asserts / throws on it.
+__global__ void bounds_check_kernel(const double *__restrict__ l, const double *__restrict__ u, size_t total, int *flag) {
+    int bad = 0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) bad |= l[k] > u[k];
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
 __global__ void peak_smem_kernel(double *out, int iters) {
     extern __shared__ __align__(16) double buf[];
     const int words = 4096; // 32 KB of doubles per CTA
@@ -312,7 +320,8 @@ struct gomp_batch {
     // per-batch storage
     DevArray<double> d_A, d_l, d_u, d_q, d_x0, d_xs, d_zs, d_ys, d_rho, d_E, d_D, d_qs, d_dy, d_dx, d_Lg, d_Ug, d_xo, d_yo, d_pri, d_dua, d_obj;
     DevArray<unsigned long long> d_prof;
-    DevArray<int> d_status, d_iters, d_rup, d_counter, d_active, d_order, d_code;
+    DevArray<int> d_status, d_iters, d_rup, d_counter, d_active, d_order, d_code, d_flag;
+    int h_flag = 0; // d_flag as of the last wait on the stream: device-resident bounds with l > u
     bool order_valid = false; // d_order holds the order derived from the previous solve of the same problems
     const int *active_src = nullptr; // per-QP mask of the next solves (device), NULL = all
     const double *A_src = nullptr, *l_src = nullptr, *u_src = nullptr, *q_src = nullptr; // borrowed device inputs
@@ -474,6 +483,15 @@ int load_data(gomp_batch *h, const double *A_val, const double *l, const double 
     if (l && u && !is_device_pointer(l) && !is_device_pointer(u) && !bounds_ordered(l, u, B * (size_t)s.m))
         return fail(GOMP_ERR_INVALID_ARGUMENT, "lower bound exceeds upper bound");
     CUDA_TRY(cudaEventRecord(h->evc0, h->stream));
+    if (l && u && is_device_pointer(l) && is_device_pointer(u)) {
+        // device-resident bounds are checked on the device; the verdict surfaces at the next gomp_batch_get / _sync
+        if (!h->d_flag.p) CUDA_TRY(h->d_flag.alloc(1));
+        CUDA_TRY(cudaMemsetAsync(h->d_flag.p, 0, sizeof(int), h->stream));
+        const size_t total = B * (size_t)s.m;
+        bounds_check_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)4 * std::max(1, h->num_sms)), 256, 0, h->stream>>>(l, u, total, h->d_flag.p);
+        CUDA_TRY(cudaGetLastError());
+        h->launches += 1;
+    }
     int rc;
     if ((rc = stage_input(h, A_val, h->d_A, B * (size_t)s.nnzA, &h->A_src))) return rc;
     if ((rc = stage_input(h, l, h->d_l, B * (size_t)s.m, &h->l_src))) return rc;
@@ -600,7 +618,7 @@ int gomp_batch_destroy(gomp_batch *h) {
     h->d_yo.release(); h->d_pri.release(); h->d_dua.release(); h->d_obj.release();
     h->d_rell.release(); h->d_cell.release(); h->d_pell.release(); h->d_cpos.release();
     h->d_ascon.release(); h->d_asocon.release(); h->d_asmeta.release(); h->d_asometa.release();
-    h->d_active.release(); h->d_order.release(); h->d_code.release(); h->d_ws.release(); h->d_row_ell.release(); h->d_col_ell.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
+    h->d_active.release(); h->d_order.release(); h->d_code.release(); h->d_flag.release(); h->d_ws.release(); h->d_row_ell.release(); h->d_col_ell.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evc0) cudaEventDestroy(h->evc0);
@@ -1036,11 +1054,20 @@ int gomp_device_memcpy(void *dst, const void *src, int64_t bytes, void *stream) 
     return GOMP_OK;
 }
 
+// wait for the handle's stream; report device-resident bounds that violated l <= u (load_data's device-side check)
+static int wait_and_check(gomp_batch *h) {
+    if (h->d_flag.p) CUDA_TRY(cudaMemcpyAsync(&h->h_flag, h->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->d_flag.p && h->h_flag)
+        return fail(GOMP_ERR_INVALID_ARGUMENT, "lower bound exceeds upper bound in the device-resident l / u of the last setup / update "
+                                               "(checked on the device; the results of solves on that data are meaningless)");
+    return GOMP_OK;
+}
+
 int gomp_batch_sync(gomp_batch *h) {
     if (!h) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return GOMP_OK;
+    return wait_and_check(h);
 }
 
 static int copy_out(gomp_batch *h, void *dst, const void *src, size_t bytes) {
@@ -1072,7 +1099,7 @@ int gomp_batch_get(gomp_batch *h, double *x, double *y, int32_t *exit_code, int3
     CUDA_TRY(cudaSetDevice(h->device));
     int rc;
     if ((rc = queue_results(h, x, y, exit_code, iters, rho_updates))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if ((rc = wait_and_check(h))) return rc;
     float ms = 0;
     if (h->launches > 0 && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_solve_ms = ms;
     else cudaGetLastError();

@@ -311,6 +311,23 @@ def test_update_rejects_bad_bounds(env):
         s.update(None, bad_l, d["u"])
     assert e.value.code == 1
     s.close()
+    # device-resident bounds (they used to go unchecked): validated on the device, reported by the next get / sync
+    import torch
+    dev = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    s = make_solver(pkg, pat, dev, settings=pkg.solver.default_settings(borrow_inputs=1), batch=2)
+    s.set_warm_start(dev["x0"])
+    good = s.solve()
+    assert (good["exit_code"] >= 0).all()
+    bad_dev = dev["l"].clone()
+    bad_dev[1, 7] = dev["u"][1, 7] + 1.0
+    s.update(None, bad_dev, dev["u"])       # asynchronous: nothing to report yet
+    s.solve_async()
+    with pytest.raises(pkg.solver.GompError) as e:
+        s.get()
+    assert e.value.code == 1
+    s.update(None, dev["l"], dev["u"])      # valid data again: the flag clears
+    s.solve()
+    s.close()
 
 
 def test_full_size_batch_properties(env):
