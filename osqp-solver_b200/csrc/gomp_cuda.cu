@@ -700,7 +700,7 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     x.slot_doubles = s.bs * s.bs + s.bs * s.ow;
     // the grouped ring (fast path of gomp_stream.cu: compile-time block size 14, uniform 2-wide off-diagonal pattern)
     // needs grp * grp_ring stage slots per warp, the generic path kStreamRing
-    const bool grouped = s.bs == 14 && h->ds.uniform_off && s.ow <= 2 && s.owT <= 2;
+    const bool grouped = (s.bs == 14 || s.bs == 12) && h->ds.uniform_off && s.ow <= 2 && s.owT <= 2; // block sizes with a compiled fast path
     auto layout = [&](bool small) {
         o = 0;
         x.small = small ? 1 : 0;
@@ -761,7 +761,7 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     const size_t half_sm = (size_t)prop.sharedMemPerMultiprocessor / 2 - 1024;
     bool cols_pack = true; // 16-bit packed column ranges: first entry < 4096, at most 15 entries
     for (uint32_t cr : s.col_range) cols_pack = cols_pack && (cr >> 8) < 4096u && (cr & 0xFFu) <= 15u;
-    const bool small_ok = s.bs % 2 == 0 && s.bs <= 32 && grouped && !std::getenv("GOMP_STREAM_NO_SMALL") && layout(true) <= half_sm &&
+    const bool small_ok = s.bs == 14 && grouped && !std::getenv("GOMP_STREAM_NO_SMALL") && layout(true) <= half_sm &&
                           cols_pack && s.m_used <= 16 * kStreamSmallThreads; // a row's rho kind: two bits of a 32-bit register per owner thread
 
     // ---- two-slot back end (gomp_duo.cu): eligibility and shared-memory layout

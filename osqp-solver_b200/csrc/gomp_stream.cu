@@ -1431,6 +1431,7 @@ cudaError_t prepare_stream(int bs, bool small, size_t smem_bytes, int *ctas_per_
         PREP((gomp_admm_stream_kernel<0, kStreamSmallThreads, true>), kStreamSmallThreads)
     }
     if (bs == 14) { PREP((gomp_admm_stream_kernel<14, kStreamThreads, false>), kStreamThreads) }
+    if (bs == 12) { PREP((gomp_admm_stream_kernel<12, kStreamThreads, false>), kStreamThreads) } // N = 6: the reference example's arm
     PREP((gomp_admm_stream_kernel<0, kStreamThreads, false>), kStreamThreads)
 #undef PREP
 }
@@ -1441,6 +1442,7 @@ cudaError_t launch_stream(const DevSym &S, const DevBatch &B, const DevSettings 
         else gomp_admm_stream_kernel<0, kStreamSmallThreads, true><<<grid, kStreamSmallThreads, smem_bytes, stream>>>(S, B, st, X);
     } else {
         if (S.bs == 14) gomp_admm_stream_kernel<14, kStreamThreads, false><<<grid, kStreamThreads, smem_bytes, stream>>>(S, B, st, X);
+        else if (S.bs == 12) gomp_admm_stream_kernel<12, kStreamThreads, false><<<grid, kStreamThreads, smem_bytes, stream>>>(S, B, st, X);
         else gomp_admm_stream_kernel<0, kStreamThreads, false><<<grid, kStreamThreads, smem_bytes, stream>>>(S, B, st, X);
     }
     return cudaGetLastError();
