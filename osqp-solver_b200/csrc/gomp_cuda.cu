@@ -296,7 +296,8 @@ struct gomp_batch {
     DevArray<uint32_t> d_asmeta, d_asometa;
     DevArray<uint32_t> d_rell, d_cell, d_pell;
     DevArray<uint16_t> d_cpos;
-    DevArray<double> d_ws;
+    DevArray<double> d_ws, d_pre;
+    int pre_cluster = 0; // streamed back end: CTAs per QP of the Ruiz cluster kernel that runs before the ADMM kernel (0 = in-kernel Ruiz)
     DevArray<uint32_t> d_row_ell;
     DevArray<uint16_t> d_col_ell;
     int device = 0, num_sms = 0, ctas_per_sm = 0, grid = 0;
@@ -618,7 +619,7 @@ int gomp_batch_destroy(gomp_batch *h) {
     h->d_yo.release(); h->d_pri.release(); h->d_dua.release(); h->d_obj.release();
     h->d_rell.release(); h->d_cell.release(); h->d_pell.release(); h->d_cpos.release();
     h->d_ascon.release(); h->d_asocon.release(); h->d_asmeta.release(); h->d_asometa.release();
-    h->d_active.release(); h->d_order.release(); h->d_code.release(); h->d_flag.release(); h->d_ws.release(); h->d_row_ell.release(); h->d_col_ell.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
+    h->d_active.release(); h->d_order.release(); h->d_code.release(); h->d_flag.release(); h->d_pre.release(); h->d_ws.release(); h->d_row_ell.release(); h->d_col_ell.release(); h->d_status.release(); h->d_iters.release(); h->d_rup.release(); h->d_counter.release(); h->d_prof.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evc0) cudaEventDestroy(h->evc0);
@@ -911,6 +912,35 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     if (h->streamed) {
         ALLOC(d_ws, (size_t)h->grid * (size_t)h->dx.stride);
         h->dx.ws = h->d_ws.p;
+        // Latency mode: when the batch leaves SMs idle, a cluster of CTAs per QP does the Ruiz equilibration ahead of the ADMM
+        // kernel (gomp_ruiz_cluster_kernel) -- 8 CTAs per QP up to SMs / 8 QPs, then 4, then 2; larger batches keep every SM
+        // busy with its own QP and equilibrate in the ADMM kernel.  GOMP_RUIZ_CLUSTER=<0|1|2|4|8> overrides (A/B runs).
+        h->dx.pre = nullptr;
+        h->pre_cluster = 0;
+        if (!h->dx.small && h->st.scaling > 0) {
+            int cs = 0;
+            for (int c : {8, 4, 2})
+                if (cs == 0 && batch * c <= (int64_t)h->num_sms) cs = c;
+            if (const char *e = std::getenv("GOMP_RUIZ_CLUSTER")) {
+                const int v = std::atoi(e);
+                cs = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0;
+            }
+            if (cs > 0) {
+                DevStream &x = h->dx;
+                long long w = 0;
+                auto wtake = [&w](long long cnt) {
+                    long long at = w;
+                    w += (cnt + 1) & ~1LL;
+                    return at;
+                };
+                x.pA = wtake(s.nnzA); x.pP = wtake(std::max<long long>(1, s.nnzPu)); x.pLo = wtake((long long)mu); x.pHi = wtake((long long)mu);
+                x.pT = wtake((long long)np); x.pW = wtake((long long)mu); x.pRed = wtake(32); x.pC = wtake(2);
+                x.pre_stride = w;
+                ALLOC(d_pre, B * (size_t)w);
+                x.pre = h->d_pre.p;
+                h->pre_cluster = cs;
+            }
+        }
     } else if (!h->ds.bounds_in_smem) {
         ALLOC(d_Lg, B * mu);
         ALLOC(d_Ug, B * mu);
@@ -992,7 +1022,14 @@ int gomp_batch_solve(gomp_batch *h) {
     CUDA_TRY(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     if (h->duo) CUDA_TRY(launch_duo(h->dd.rpt, h->dd.cpt, s.bs, h->ds, h->db, h->dst, h->dd, h->grid, h->smem_bytes, h->stream));
-    else if (h->streamed) CUDA_TRY(launch_stream(h->ds, h->db, h->dst, h->dx, h->grid, h->smem_bytes, h->stream));
+    else if (h->streamed) {
+        if (h->pre_cluster > 0) {
+            const int clusters = (int)std::max<int64_t>(1, std::min<int64_t>(h->batch, h->num_sms / h->pre_cluster));
+            CUDA_TRY(launch_prescale(h->ds, h->db, h->dst, h->dx, clusters, h->pre_cluster, h->stream));
+            h->launches += 1;
+        }
+        CUDA_TRY(launch_stream(h->ds, h->db, h->dst, h->dx, h->grid, h->smem_bytes, h->stream));
+    }
     else CUDA_TRY(h->kernel.launch(h->ds, h->db, h->dst, h->grid, h->smem_bytes, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     // queue order of the next solve, should it be a warm re-solve of the same problems (gomp_batch_update)

@@ -23,6 +23,8 @@
 
 #include "gomp_stream.h"
 
+#include <cooperative_groups.h>
+
 namespace gomp_dev {
 
 namespace {
@@ -585,22 +587,32 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
         long long t_phase = clock64();
 
         // ------------------------------------------------------------------ load
-        {
+        // X.pre: the cluster kernel below has already equilibrated this QP (scaled A, P, bounds in its buffers; D, E, q in
+        // their per-QP arrays) -- the load is a copy and the Ruiz phase is skipped
+        const double *const preq = X.pre != nullptr ? X.pre + (size_t)b * X.pre_stride : nullptr;
+        const double *gl = B.l + (size_t)b * S.m, *gu = B.u + (size_t)b * S.m;
+        if (preq != nullptr) {
+            for (int k = tid; k < S.nnzA; k += kST) gA[k] = __ldcg(preq + X.pA + k);
+            for (int k = tid; k < S.nnzPu; k += kST) gP[k] = __ldcg(preq + X.pP + k);
+            for (int i = tid; i < mu; i += kST) {
+                gLo[i] = __ldcg(preq + X.pLo + i);
+                gHi[i] = __ldcg(preq + X.pHi + i);
+            }
+        } else {
             const double *srcA = B.A_val + (size_t)b * B.A_pitch;
             for (int k = tid; k < S.nnzA; k += kST) gA[k] = srcA[k];
             for (int k = tid; k < S.nnzPu; k += kST) gP[k] = S.Pu_val[k];
-        }
-        const double *gl = B.l + (size_t)b * S.m, *gu = B.u + (size_t)b * S.m;
-        for (int i = tid; i < mu; i += kST) {
-            const int orig = S.used_rows[i];
-            gLo[i] = fmax(gl[orig], -kInfty);
-            gHi[i] = fmin(gu[orig], kInfty);
-            gE[i] = 1.0;
-        }
-        for (int p = tid; p < np; p += kST) {
-            const int var = S.pos_var[p];
-            gD[p] = 1.0;
-            if (hasq) gq[p] = var >= 0 ? B.q[(size_t)b * S.n + var] : 0.0;
+            for (int i = tid; i < mu; i += kST) {
+                const int orig = S.used_rows[i];
+                gLo[i] = fmax(gl[orig], -kInfty);
+                gHi[i] = fmin(gu[orig], kInfty);
+                gE[i] = 1.0;
+            }
+            for (int p = tid; p < np; p += kST) {
+                const int var = S.pos_var[p];
+                gD[p] = 1.0;
+                if (hasq) gq[p] = var >= 0 ? B.q[(size_t)b * S.n + var] : 0.0;
+            }
         }
         double bad[1] = {0.0};
         for (int e = tid; e < S.n_empty; e += kST) {
@@ -616,6 +628,10 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
         // factors of a pass are kept in shared memory while it runs when they fit the regions that are idle before the
         // first iteration -- the right-hand side (P values) and the factor ring (patterns, column factors); otherwise
         // they are read from the workspace / pattern arrays in L2.
+        double cscale = 1.0;
+        if (preq != nullptr) {
+            cscale = __ldcg(preq + X.pC);
+        } else {
         const bool pscr = X.p_scratch != 0;
         double *const Pv = pscr ? sRHS : gP;
         double *const dtv = pscr ? sRing : gT;
@@ -642,7 +658,6 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             for (int q = pfptr[p_], q1 = pfptr[p_ + 1]; q < q1; ++q) nrm = fmax(nrm, fabs(Pv[pfent[q] & 0xFFFFu]));
             return nrm;
         };
-        double cscale = 1.0;
 #pragma unroll 1
         for (int it = 0; it < st.scaling; ++it) {
             COLS2(p, p2, two) {
@@ -708,6 +723,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             gLo[i] *= gE[i];
             gHi[i] *= gE[i];
         }
+        } // (in-kernel Ruiz)
         const double cinv = 1.0 / cscale;
         const bool uns = !st.scaled_termination;
         SMARK(PH_SCALE);
@@ -1417,6 +1433,162 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
         __syncthreads();
         SMARK(PH_STORE);
     }
+}
+
+// ================================================================================================
+//          Ruiz equilibration by a thread-block CLUSTER per QP (long horizons, small batches)
+// ================================================================================================
+// A long-horizon QP alone on its SM spends a quarter of its solve in the ten Ruiz passes: five strided traversals of A per
+// pass against one SM's L2 port (2.9 M of 10.9 M cycles at H = 400).  When the batch leaves SMs idle (batch x cluster size <=
+// SM count), this kernel runs first: a cluster of up to 8 CTAs per QP, every thread owning a few rows and columns, the
+// phases of a pass separated by the hardware cluster barrier (barrier.cluster, arrive.release / wait.acquire) instead of
+// __syncthreads.  It performs the very operations of the in-kernel phase on the same pattern arrays -- max norms are order
+// independent and every entry is scaled row factor first, column factor second, as there -- and leaves the scaled A, P, l, u
+// and the cost scale in per-QP buffers (X.pre), D, E and the scaled q in their per-QP arrays; the ADMM kernel then loads
+// instead of scaling.  Only the cost normalisation's mean of the column norms of P is summed in a different order (per CTA,
+// then over the cluster's CTAs in rank order): last-bit differences in c, as between any two summation trees.
+__global__ void __launch_bounds__(kStreamThreads, 1) gomp_ruiz_cluster_kernel(const __grid_constant__ DevSym S, const __grid_constant__ DevBatch B,
+                                                                               const __grid_constant__ DevSettings st,
+                                                                               const __grid_constant__ DevStream X) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double sRed[2 * (kStreamThreads / 32)];
+    const int tid = threadIdx.x;
+    const int nb = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int gt = rank * kStreamThreads + tid, GT = nb * kStreamThreads;
+    const int nclusters = (int)gridDim.x / nb, cid = (int)blockIdx.x / nb;
+    const int np = S.n_pad, mu = S.m_used;
+    const bool hasq = B.q != nullptr;
+    auto csync = [&]() {
+        __threadfence(); // (the barrier's release / acquire pair orders the cluster's global-memory traffic; belt and braces)
+        cluster.sync();
+    };
+    for (int b = cid; b < B.batch; b += nclusters) {
+        if (B.active != nullptr && B.active[b] == 0) continue; // (uniform over the cluster)
+        double *const pre = X.pre + (size_t)b * X.pre_stride;
+        double *const A = pre + X.pA, *const P = pre + X.pP, *const Lo = pre + X.pLo, *const Hi = pre + X.pHi, *const dt = pre + X.pT,
+                     *const et = pre + X.pW, *const red = pre + X.pRed;
+        double *const E = B.Eg + (size_t)b * mu, *const D = B.Dg + (size_t)b * np;
+        double *const q = hasq ? B.qs + (size_t)b * np : nullptr;
+        // ---- load (as the ADMM kernel's load phase)
+        {
+            const double *srcA = B.A_val + (size_t)b * B.A_pitch;
+            for (int k = gt; k < S.nnzA; k += GT) __stcg(A + k, srcA[k]);
+            for (int k = gt; k < S.nnzPu; k += GT) __stcg(P + k, S.Pu_val[k]);
+            const double *gl = B.l + (size_t)b * S.m, *gu = B.u + (size_t)b * S.m;
+            for (int i = gt; i < mu; i += GT) {
+                const int orig = S.used_rows[i];
+                __stcg(Lo + i, fmax(gl[orig], -kInfty));
+                __stcg(Hi + i, fmin(gu[orig], kInfty));
+                __stcg(E + i, 1.0);
+            }
+            for (int p = gt; p < np; p += GT) {
+                const int var = S.pos_var[p];
+                __stcg(D + p, 1.0);
+                if (hasq) __stcg(q + p, var >= 0 ? B.q[(size_t)b * S.n + var] : 0.0);
+            }
+        }
+        csync();
+        auto pf_absmax = [&](int p) {
+            double nrm = 0.0;
+            for (int k = __ldg(S.pf_ptr + p), k1 = __ldg(S.pf_ptr + p + 1); k < k1; ++k) nrm = fmax(nrm, fabs(__ldcg(P + (__ldg(S.pf_csr + k) & 0xFFFFu))));
+            return nrm;
+        };
+        double cscale = 1.0;
+#pragma unroll 1
+        for (int it = 0; it < st.scaling; ++it) {
+            // ---- norms of the KKT columns: variables (P and A columns), constraints (A rows)
+            for (int p = gt; p < np; p += GT) {
+                const uint32_t rg = __ldg(S.col_range + p);
+                double na = 0.0;
+                for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) na = fmax(na, fabs(__ldcg(A + k)));
+                __stcg(dt + p, 1.0 / sqrt(limit_scaling(fmax(pf_absmax(p), na))));
+            }
+            for (int i = gt; i < mu; i += GT) {
+                const uint32_t rg = __ldg(S.row_range + i);
+                double na = 0.0;
+                for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) na = fmax(na, fabs(__ldcg(A + (__ldg(S.row_csr + k) & 0xFFFFu))));
+                __stcg(et + i, 1.0 / sqrt(limit_scaling(na)));
+            }
+            csync();
+            // ---- rows of A and E by the row factors, P by the column factors on both sides
+            for (int i = gt; i < mu; i += GT) {
+                const uint32_t rg = __ldg(S.row_range + i);
+                const double ea = __ldcg(et + i);
+                for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) {
+                    double *a = A + (__ldg(S.row_csr + k) & 0xFFFFu);
+                    __stcg(a, __ldcg(a) * ea);
+                }
+                __stcg(E + i, __ldcg(E + i) * ea);
+            }
+            for (int k = gt; k < S.nnzPu; k += GT) {
+                const uint32_t ij = __ldg(S.Pu_ij + k);
+                __stcg(P + k, (__ldcg(P + k) * __ldcg(dt + (ij >> 16))) * __ldcg(dt + (ij & 0xFFFFu)));
+            }
+            csync();
+            // ---- columns of A, D and q by the column factors; cost normalisation from the scaled P
+            double psum = 0.0, qn = 0.0;
+            for (int p = gt; p < np; p += GT) {
+                const uint32_t rg = __ldg(S.col_range + p);
+                const double da = __ldcg(dt + p);
+                for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) __stcg(A + k, __ldcg(A + k) * da);
+                __stcg(D + p, __ldcg(D + p) * da);
+                if (hasq) {
+                    const double qv = __ldcg(q + p) * da;
+                    __stcg(q + p, qv);
+                    qn = fmax(qn, fabs(qv));
+                }
+                psum += pf_absmax(p);
+            }
+            psum = block_sum<kStreamThreads>(psum, sRed, tid);
+            {
+                double qv[1] = {qn};
+                block_max<1, kStreamThreads>(qv, sRed, tid);
+                qn = qv[0];
+            }
+            if (tid == 0) {
+                __stcg(red + rank, psum);
+                __stcg(red + 16 + rank, qn);
+            }
+            csync();
+            double ps = 0.0, qm = 0.0;
+            for (int r = 0; r < nb; ++r) {
+                ps += __ldcg(red + r);
+                qm = fmax(qm, __ldcg(red + 16 + r));
+            }
+            double ct = fmax(ps / (double)S.n, limit_scaling(qm));
+            ct = 1.0 / limit_scaling(ct);
+            for (int k = gt; k < S.nnzPu; k += GT) __stcg(P + k, __ldcg(P + k) * ct);
+            if (hasq)
+                for (int p = gt; p < np; p += GT) __stcg(q + p, __ldcg(q + p) * ct);
+            cscale *= ct;
+            csync();
+        }
+        for (int i = gt; i < mu; i += GT) {
+            const double e = __ldcg(E + i);
+            __stcg(Lo + i, __ldcg(Lo + i) * e);
+            __stcg(Hi + i, __ldcg(Hi + i) * e);
+        }
+        if (gt == 0) __stcg(pre + X.pC, cscale);
+        csync(); // (the next QP of this cluster reuses nothing, but keeps the CTAs of the cluster in step)
+    }
+}
+
+cudaError_t launch_prescale(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int clusters, int cluster_size,
+                            cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * cluster_size), 1, 1);
+    cfg.blockDim = dim3(kStreamThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gomp_ruiz_cluster_kernel, S, B, st, X);
 }
 
 cudaError_t prepare_stream(int bs, bool small, size_t smem_bytes, int *ctas_per_sm) {

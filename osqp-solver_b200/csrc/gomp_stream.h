@@ -31,6 +31,11 @@ struct DevStream {
     int p_scratch;     // the P side of the Ruiz scaling fits the idle right-hand side / ring regions (shared memory)
     int small;         // small-QP mode: A values, w and the CSR / CSC pattern arrays in shared memory, 256 threads per CTA
     int oA, oW, oRowEnt, oRowRange, oColRange, oCscRow; // ... their byte offsets
+    // Ruiz equilibration done beforehand by a cluster of CTAs per QP (gomp_ruiz_cluster_kernel; NULL = in-kernel): per-QP buffers
+    // [batch][pre_stride] with the scaled A values, triu(P), bounds, the pass's column / row factors, the cluster's reduction
+    // slots and the cost scale (offsets in doubles)
+    double *pre;
+    long long pre_stride, pA, pP, pLo, pHi, pT, pW, pRed, pC;
     int slot_doubles; // bs*bs + bs*ow, one ring slot
     int ring_doubles; // ring size per substitution warp
 };
@@ -38,6 +43,9 @@ struct DevStream {
 cudaError_t prepare_stream(int bs, bool small, size_t smem_bytes, int *ctas_per_sm);
 cudaError_t launch_stream(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int grid, size_t smem_bytes,
                           cudaStream_t stream);
+// the cluster kernel: `clusters` clusters of `cluster_size` CTAs (1, 2, 4 or 8), QPs dealt round-robin to the clusters
+cudaError_t launch_prescale(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int clusters, int cluster_size,
+                            cudaStream_t stream);
 
 } // namespace gomp_dev
 #endif
