@@ -297,6 +297,7 @@ struct gomp_batch {
     DevArray<uint32_t> d_rell, d_cell, d_pell;
     DevArray<uint16_t> d_cpos;
     DevArray<double> d_ws, d_pre;
+    int solve_cluster = 1; // streamed back end: CTAs per QP of the ADMM kernel itself (helpers share the sparse passes)
     int pre_cluster = 0; // streamed back end: CTAs per QP of the Ruiz cluster kernel that runs before the ADMM kernel (0 = in-kernel Ruiz)
     DevArray<uint32_t> d_row_ell;
     DevArray<uint16_t> d_col_ell;
@@ -910,11 +911,10 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     ALLOC(d_D, B * np);
     ALLOC(d_dx, B * np);
     if (h->streamed) {
-        ALLOC(d_ws, (size_t)h->grid * (size_t)h->dx.stride);
-        h->dx.ws = h->d_ws.p;
-        // Latency mode: when the batch leaves SMs idle, a cluster of CTAs per QP does the Ruiz equilibration ahead of the ADMM
-        // kernel (gomp_ruiz_cluster_kernel) -- 8 CTAs per QP up to SMs / 8 QPs, then 4, then 2; larger batches keep every SM
-        // busy with its own QP and equilibrate in the ADMM kernel.  GOMP_RUIZ_CLUSTER=<0|1|2|4|8> overrides (A/B runs).
+        // Latency mode: when the batch leaves SMs idle, a QP is served by a CLUSTER of CTAs -- 8 per QP up to SMs / 8 QPs, then 4,
+        // then 2: the Ruiz equilibration runs as a cluster kernel ahead of the ADMM kernel (gomp_ruiz_cluster_kernel), and the ADMM
+        // kernel itself is launched with that cluster size, the extra CTAs sharing the sparse passes of every iteration
+        // (gomp_stream.cu).  Larger batches keep every SM busy with its own QP.  GOMP_RUIZ_CLUSTER=<0|1|2|4|8> overrides (A/B runs).
         h->dx.pre = nullptr;
         h->pre_cluster = 0;
         if (!h->dx.small && h->st.scaling > 0) {
@@ -925,21 +925,25 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
                 const int v = std::atoi(e);
                 cs = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0;
             }
-            if (cs > 0) {
-                DevStream &x = h->dx;
-                long long w = 0;
-                auto wtake = [&w](long long cnt) {
-                    long long at = w;
-                    w += (cnt + 1) & ~1LL;
-                    return at;
-                };
-                x.pA = wtake(s.nnzA); x.pP = wtake(std::max<long long>(1, s.nnzPu)); x.pLo = wtake((long long)mu); x.pHi = wtake((long long)mu);
-                x.pT = wtake((long long)np); x.pW = wtake((long long)mu); x.pRed = wtake(32); x.pC = wtake(2);
-                x.pre_stride = w;
-                ALLOC(d_pre, B * (size_t)w);
-                x.pre = h->d_pre.p;
-                h->pre_cluster = cs;
-            }
+            h->pre_cluster = cs;
+        }
+        h->solve_cluster = h->pre_cluster > 1 && !std::getenv("GOMP_NO_SOLVE_CLUSTER") ? h->pre_cluster : 1;
+        if (h->solve_cluster > 1) h->grid = (int)std::max<int64_t>(1, std::min<int64_t>(batch, h->num_sms / h->solve_cluster)) * h->solve_cluster;
+        ALLOC(d_ws, (size_t)h->grid * (size_t)h->dx.stride);
+        h->dx.ws = h->d_ws.p;
+        if (h->pre_cluster > 0) {
+            DevStream &x = h->dx;
+            long long w = 0;
+            auto wtake = [&w](long long cnt) {
+                long long at = w;
+                w += (cnt + 1) & ~1LL;
+                return at;
+            };
+            x.pA = wtake(s.nnzA); x.pP = wtake(std::max<long long>(1, s.nnzPu)); x.pLo = wtake((long long)mu); x.pHi = wtake((long long)mu);
+            x.pT = wtake((long long)np); x.pW = wtake((long long)mu); x.pRed = wtake(32); x.pC = wtake(2);
+            x.pre_stride = w;
+            ALLOC(d_pre, B * (size_t)w);
+            x.pre = h->d_pre.p;
         }
     } else if (!h->ds.bounds_in_smem) {
         ALLOC(d_Lg, B * mu);
@@ -1028,7 +1032,7 @@ int gomp_batch_solve(gomp_batch *h) {
             CUDA_TRY(launch_prescale(h->ds, h->db, h->dst, h->dx, clusters, h->pre_cluster, h->stream));
             h->launches += 1;
         }
-        CUDA_TRY(launch_stream(h->ds, h->db, h->dst, h->dx, h->grid, h->smem_bytes, h->stream));
+        CUDA_TRY(launch_stream(h->ds, h->db, h->dst, h->dx, h->grid, h->solve_cluster, h->smem_bytes, h->stream));
     }
     else CUDA_TRY(h->kernel.launch(h->ds, h->db, h->dst, h->grid, h->smem_bytes, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));

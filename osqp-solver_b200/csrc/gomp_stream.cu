@@ -19,6 +19,7 @@
 //
 // Replaces the same reference calls as the resident kernel (src/osqp-wrapper.h:28,36,40,46,52); the
 // algorithm follows oracle/osqp_ref.c phase by phase (tests/cpp/emulate.cpp is its sequential model).
+#include <algorithm>
 #include <cstdlib>
 
 #include "gomp_stream.h"
@@ -442,8 +443,20 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
     // kind sits in two bits of its owner's `rtype` register, so the update never fetches rho from L2 nor divides by it
     double *const sRhoTab = reinterpret_cast<double *>(smem_raw + X.oBar + 8 * 4 * kStreamRing + 16);
 
-    // per-CTA workspace (global, L2-resident)
-    double *const ws = X.ws + (size_t)blockIdx.x * X.stride;
+    // A QP may be served by a CLUSTER of CTAs (long horizons, batches that leave SMs idle; launch_stream): rank 0 -- the leader --
+    // runs the whole algorithm as a lone CTA would; the other CTAs are helpers that take their share of the two sparse passes
+    // of every iteration (right-hand side gather, x / z / y update), reading x~ from and writing the right-hand side to the
+    // leader's shared memory through distributed shared memory.  ct / CT: this thread among the cluster's threads.
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = SM ? 1 : (int)cluster.num_blocks(), crank = SM ? 0 : (int)cluster.block_rank();
+    const int ct = crank * kST + tid, CT = cs * kST;
+    auto csync = [&]() {
+        __threadfence(); // (global-memory results of this CTA: ordered by the barrier's release / acquire pair; belt and braces)
+        cluster.sync();
+    };
+    // per-cluster workspace (global, L2-resident)
+    double *const ws = X.ws + (size_t)(SM ? (int)blockIdx.x : (int)blockIdx.x / cs) * X.stride;
     double *const gA = SM ? reinterpret_cast<double *>(smem_raw + X.oA) : ws + X.wA;
     double *const gW = SM ? reinterpret_cast<double *>(smem_raw + X.oW) : ws + X.wW;
     double *const gP = ws + X.wP, *const gRho = ws + X.wRho, *const gDinv = ws + X.wDinv,
@@ -472,6 +485,82 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             sColPk[k] = (uint16_t)((cr >> 8) | ((cr & 0xFFu) << 12));
         }
         for (int k = tid; k <= mu; k += kST) sRowPtr[k] = S.row_ptr[k];
+    }
+    // ---- the two passes a cluster shares (one CTA: ct = tid, CT = kST -- the plain strided loops)
+    enum { OP_RHS = 1, OP_UPDATE = 2, OP_EXIT = 3 };
+    volatile int *const sCtl = reinterpret_cast<volatile int *>(sRhoTab); // leader -> helpers: {op, problem, do_info} (region unused outside the small-QP mode)
+    // rhs = sigma x - q + A'(rho z - y), columns ct, ct + CT, ...; dst = the leader's right-hand side vector
+    auto rhs_share = [&](const double *gx_, const double *gq_, double *dst, bool hasq_) {
+        for (int p = ct; p < np; p += 2 * CT) {
+            const bool two = p + CT < np;
+            const int p2 = two ? p + CT : p;
+            double ra = st.sigma * gx_[p], rb = st.sigma * gx_[p2];
+            if (hasq_) {
+                ra -= gq_[p];
+                rb -= gq_[p2];
+            }
+            col_dot_ell2(S, X, np, p, p2, gA, gW, ra, rb);
+            dst[p] = ra;
+            if (two) dst[p2] = rb;
+        }
+    };
+    // x <- alpha x~ + (1 - alpha) x;  z~ = A x~, projection, dual step, w = rho z - y; rows ct, ct + CT, ...; src = x~ (leader's)
+    auto update_share = [&](double *gx_, double *gz_, double *gy_, double *gdy_, double *gdx_, const double *src, bool do_info_, bool hasq_) {
+        for (int p = ct; p < np; p += CT) {
+            const double xo = gx_[p];
+            const double xn = st.alpha * src[p] + (1.0 - st.alpha) * xo;
+            if (do_info_ && hasq_) gdx_[p] = xn - xo;
+            gx_[p] = xn;
+        }
+        for (int i = ct; i < mu; i += 2 * CT) {
+            const bool two = i + CT < mu;
+            const int i2 = two ? i + CT : i;
+            double zta, ztb;
+            row_dot_ell2(X, mu, i, i2, gA, src, zta, ztb);
+            const double rva = gRho[i], zoa = gz_[i], yoa = gy_[i], loa = gLo[i], hia = gHi[i];
+            const double rvb = gRho[i2], zob = gz_[i2], yob = gy_[i2], lob = gLo[i2], hib = gHi[i2];
+            {
+                const double zr = st.alpha * zta + (1.0 - st.alpha) * zoa;
+                const double zn = fmin(fmax(zr + (1.0 / rva) * yoa, loa), hia);
+                const double d = rva * (zr - zn), yn = yoa + d;
+                gy_[i] = yn;
+                gz_[i] = zn;
+                gW[i] = fma(rva, zn, -yn); // w = rho z - y for the next gather
+                if (do_info_) gdy_[i] = d;
+            }
+            if (two) {
+                const double zr = st.alpha * ztb + (1.0 - st.alpha) * zob;
+                const double zn = fmin(fmax(zr + (1.0 / rvb) * yob, lob), hib);
+                const double d = rvb * (zr - zn), yn = yob + d;
+                gy_[i2] = yn;
+                gz_[i2] = zn;
+                gW[i2] = fma(rvb, zn, -yn);
+                if (do_info_) gdy_[i2] = d;
+            }
+        }
+    };
+    if constexpr (!SM) {
+        if (crank != 0) {
+            // ---- helper CTA: serve the leader's passes until it says exit.  Two cluster barriers per pass: "operation published"
+            // and "operation complete"; the leader's control words and x~ / right-hand side are read and written in ITS shared memory.
+            const volatile int *lctl = cluster.map_shared_rank(const_cast<int *>(reinterpret_cast<volatile int *>(sRhoTab)), 0);
+            double *lRHS = cluster.map_shared_rank(sRHS, 0);
+            for (;;) {
+                csync();
+                const int op = lctl[0];
+                if (op == OP_EXIT) {
+                    csync(); // (the leader's shared memory stays valid until every helper has read the word)
+                    break;
+                }
+                const int hb = lctl[1];
+                const bool hinfo = lctl[2] != 0, hq = B.q != nullptr;
+                const size_t hmu = (size_t)hb * mu, hnp = (size_t)hb * np;
+                if (op == OP_RHS) rhs_share(B.x_state + hnp, hq ? B.qs + hnp : nullptr, lRHS, hq);
+                else update_share(B.x_state + hnp, B.z_state + hmu, B.y_state + hmu, B.dyg + hmu, B.dxg + hnp, lRHS, hinfo, hq);
+                csync();
+            }
+            return;
+        }
     }
     if (tid == 0) {
         for (int k = 0; k < 4 * kStreamRing; ++k) mbar_init(sFull + k, 1);
@@ -902,16 +991,15 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                     }
                 }
             } else {
-                COLS2(p, p2, two) {
-                    double ra = st.sigma * gx[p], rb = st.sigma * gx[p2];
-                    if (hasq) {
-                        ra -= gq[p];
-                        rb -= gq[p2];
+                if (cs > 1) {
+                    if (tid == 0) {
+                        sCtl[0] = OP_RHS;
+                        sCtl[1] = b;
                     }
-                    col_dot2(p, p2, gW, ra, rb);
-                    sRHS[p] = ra;
-                    if (two) sRHS[p2] = rb;
+                    csync();
                 }
+                rhs_share(gx, gq, sRHS, hasq);
+                if (cs > 1) csync();
             }
             __syncthreads();
             SMARK(PH_RHS);
@@ -1200,36 +1288,16 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                     }
                 }
             } else {
-                for (int p = tid; p < np; p += kST) {
-                    const double xo = gx[p];
-                    const double xn = st.alpha * sRHS[p] + (1.0 - st.alpha) * xo;
-                    if (do_info && hasq) gdx[p] = xn - xo;
-                    gx[p] = xn;
-                }
-                ROWS2(i, i2, two) {
-                    double zta, ztb;
-                    row_dot2(i, i2, sRHS, zta, ztb);
-                    const double rva = gRho[i], zoa = gz[i], yoa = gy[i], loa = gLo[i], hia = gHi[i];
-                    const double rvb = gRho[i2], zob = gz[i2], yob = gy[i2], lob = gLo[i2], hib = gHi[i2];
-                    {
-                        const double zr = st.alpha * zta + (1.0 - st.alpha) * zoa;
-                        const double zn = fmin(fmax(zr + (1.0 / rva) * yoa, loa), hia);
-                        const double d = rva * (zr - zn), yn = yoa + d;
-                        gy[i] = yn;
-                        gz[i] = zn;
-                        gW[i] = fma(rva, zn, -yn); // w = rho z - y for the next gather
-                        if (do_info) gdy[i] = d;
+                if (cs > 1) {
+                    if (tid == 0) {
+                        sCtl[0] = OP_UPDATE;
+                        sCtl[1] = b;
+                        sCtl[2] = do_info ? 1 : 0;
                     }
-                    if (two) {
-                        const double zr = st.alpha * ztb + (1.0 - st.alpha) * zob;
-                        const double zn = fmin(fmax(zr + (1.0 / rvb) * yob, lob), hib);
-                        const double d = rvb * (zr - zn), yn = yob + d;
-                        gy[i2] = yn;
-                        gz[i2] = zn;
-                        gW[i2] = fma(rvb, zn, -yn);
-                        if (do_info) gdy[i2] = d;
-                    }
+                    csync();
                 }
+                update_share(gx, gz, gy, gdy, gdx, sRHS, do_info, hasq);
+                if (cs > 1) csync();
             }
             __syncthreads();
             SMARK(PH_UPDATE);
@@ -1433,6 +1501,11 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
         __syncthreads();
         SMARK(PH_STORE);
     }
+    if (cs > 1) { // release the helpers; they read the word in this CTA's shared memory, so wait until they have
+        if (tid == 0) sCtl[0] = OP_EXIT;
+        csync();
+        csync();
+    }
 }
 
 // ================================================================================================
@@ -1607,17 +1680,27 @@ cudaError_t prepare_stream(int bs, bool small, size_t smem_bytes, int *ctas_per_
     PREP((gomp_admm_stream_kernel<0, kStreamThreads, false>), kStreamThreads)
 #undef PREP
 }
-cudaError_t launch_stream(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int grid, size_t smem_bytes,
-                          cudaStream_t stream) {
+cudaError_t launch_stream(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int grid, int cluster_size,
+                          size_t smem_bytes, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)(X.small ? kStreamSmallThreads : kStreamThreads), 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)(X.small ? 1 : std::max(1, cluster_size));
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (X.small) {
-        if (S.bs == 14) gomp_admm_stream_kernel<14, kStreamSmallThreads, true><<<grid, kStreamSmallThreads, smem_bytes, stream>>>(S, B, st, X);
-        else gomp_admm_stream_kernel<0, kStreamSmallThreads, true><<<grid, kStreamSmallThreads, smem_bytes, stream>>>(S, B, st, X);
-    } else {
-        if (S.bs == 14) gomp_admm_stream_kernel<14, kStreamThreads, false><<<grid, kStreamThreads, smem_bytes, stream>>>(S, B, st, X);
-        else if (S.bs == 12) gomp_admm_stream_kernel<12, kStreamThreads, false><<<grid, kStreamThreads, smem_bytes, stream>>>(S, B, st, X);
-        else gomp_admm_stream_kernel<0, kStreamThreads, false><<<grid, kStreamThreads, smem_bytes, stream>>>(S, B, st, X);
+        if (S.bs == 14) return cudaLaunchKernelEx(&cfg, gomp_admm_stream_kernel<14, kStreamSmallThreads, true>, S, B, st, X);
+        return cudaLaunchKernelEx(&cfg, gomp_admm_stream_kernel<0, kStreamSmallThreads, true>, S, B, st, X);
     }
-    return cudaGetLastError();
+    if (S.bs == 14) return cudaLaunchKernelEx(&cfg, gomp_admm_stream_kernel<14, kStreamThreads, false>, S, B, st, X);
+    if (S.bs == 12) return cudaLaunchKernelEx(&cfg, gomp_admm_stream_kernel<12, kStreamThreads, false>, S, B, st, X);
+    return cudaLaunchKernelEx(&cfg, gomp_admm_stream_kernel<0, kStreamThreads, false>, S, B, st, X);
 }
 
 } // namespace gomp_dev
