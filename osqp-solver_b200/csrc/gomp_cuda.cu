@@ -297,6 +297,7 @@ struct gomp_batch {
     DevArray<uint32_t> d_rell, d_cell, d_pell;
     DevArray<uint16_t> d_cpos;
     DevArray<double> d_ws, d_pre;
+    int max_clusters = 0;  // ... and how many such clusters are resident at once
     int solve_cluster = 1; // streamed back end: CTAs per QP of the ADMM kernel itself (helpers share the sparse passes)
     int pre_cluster = 0; // streamed back end: CTAs per QP of the Ruiz cluster kernel that runs before the ADMM kernel (0 = in-kernel Ruiz)
     DevArray<uint32_t> d_row_ell;
@@ -919,8 +920,14 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
         h->pre_cluster = 0;
         if (!h->dx.small && h->st.scaling > 0) {
             int cs = 0;
-            for (int c : {8, 4, 2})
-                if (cs == 0 && batch * c <= (int64_t)h->num_sms) cs = c;
+            for (int c : {8, 4, 2}) {
+                int fit = 0; // clusters of c CTAs the device holds at once (a cluster lives inside one GPC: fewer than SMs / c)
+                if (cs == 0 && stream_max_clusters(s.bs, c, h->smem_bytes, &fit) == cudaSuccess && batch <= (int64_t)fit) {
+                    cs = c;
+                    h->max_clusters = fit;
+                }
+                cudaGetLastError();
+            }
             if (const char *e = std::getenv("GOMP_RUIZ_CLUSTER")) {
                 const int v = std::atoi(e);
                 cs = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0;
@@ -928,7 +935,7 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
             h->pre_cluster = cs;
         }
         h->solve_cluster = h->pre_cluster > 1 && !std::getenv("GOMP_NO_SOLVE_CLUSTER") ? h->pre_cluster : 1;
-        if (h->solve_cluster > 1) h->grid = (int)std::max<int64_t>(1, std::min<int64_t>(batch, h->num_sms / h->solve_cluster)) * h->solve_cluster;
+        if (h->solve_cluster > 1) h->grid = (int)std::max<int64_t>(1, std::min<int64_t>(batch, h->max_clusters > 0 ? h->max_clusters : h->num_sms / h->solve_cluster)) * h->solve_cluster;
         ALLOC(d_ws, (size_t)h->grid * (size_t)h->dx.stride);
         h->dx.ws = h->d_ws.p;
         if (h->pre_cluster > 0) {
@@ -1028,7 +1035,7 @@ int gomp_batch_solve(gomp_batch *h) {
     if (h->duo) CUDA_TRY(launch_duo(h->dd.rpt, h->dd.cpt, s.bs, h->ds, h->db, h->dst, h->dd, h->grid, h->smem_bytes, h->stream));
     else if (h->streamed) {
         if (h->pre_cluster > 0) {
-            const int clusters = (int)std::max<int64_t>(1, std::min<int64_t>(h->batch, h->num_sms / h->pre_cluster));
+            const int clusters = (int)std::max<int64_t>(1, std::min<int64_t>(h->batch, h->max_clusters > 0 ? h->max_clusters : h->num_sms / h->pre_cluster));
             CUDA_TRY(launch_prescale(h->ds, h->db, h->dst, h->dx, clusters, h->pre_cluster, h->stream));
             h->launches += 1;
         }

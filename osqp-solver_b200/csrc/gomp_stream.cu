@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
         for (int k = tid; k <= mu; k += kST) sRowPtr[k] = S.row_ptr[k];
     }
     // ---- the two passes a cluster shares (one CTA: ct = tid, CT = kST -- the plain strided loops)
-    enum { OP_RHS = 1, OP_UPDATE = 2, OP_EXIT = 3 };
+    enum { OP_RHS = 1, OP_UPDATE = 2, OP_EXIT = 3, OP_ASSEMBLE = 4 };
     volatile int *const sCtl = reinterpret_cast<volatile int *>(sRhoTab); // leader -> helpers: {op, problem, do_info} (region unused outside the small-QP mode)
     // rhs = sigma x - q + A'(rho z - y), columns ct, ct + CT, ...; dst = the leader's right-hand side vector
     auto rhs_share = [&](const double *gx_, const double *gq_, double *dst, bool hasq_) {
@@ -539,6 +539,37 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             }
         }
     };
+    // S = P + sigma I + A' diag(rho) A: packed diagonal-block entries and off-diagonal entries ct, ct + CT, ... into the workspace
+    auto assemble_share = [&]() {
+        const int dpb = bs * (bs + 1) / 2, ndiag = T * dpb;
+        for (int e = ct; e < ndiag; e += CT) {
+            double acc = 0.0;
+            const uint32_t q1 = __ldg(S.sd_ptr + e + 1);
+            for (uint32_t q = __ldg(S.sd_ptr + e); q < q1; ++q) {
+                const gomp::Contrib cn = S.sd_con[q];
+                acc += gRho[cn.row] * gA[cn.k1] * gA[cn.k2];
+            }
+            const uint16_t pk = __ldg(S.sd_pk + e);
+            if (pk != 0xFFFFu) acc += gP[pk];
+            const int kind = __ldg(S.sd_kind + e);
+            if (kind == 1) acc += st.sigma;
+            else if (kind == 2) acc = 1.0;
+            const int t = e / dpb, rc = __ldg(S.tri_rc + (e - t * dpb)), rw = rc >> 8, c = rc & 0xFF;
+            gDinv[(size_t)t * bb + rw * bs + c] = acc;
+            gDinv[(size_t)t * bb + c * bs + rw] = acc;
+        }
+        for (int e = ct; e < S.noff; e += CT) {
+            double acc = 0.0;
+            const uint32_t q1 = __ldg(S.so_ptr + e + 1);
+            for (uint32_t q = __ldg(S.so_ptr + e); q < q1; ++q) {
+                const gomp::Contrib cn = S.so_con[q];
+                acc += gRho[cn.row] * gA[cn.k1] * gA[cn.k2];
+            }
+            const uint16_t pk = __ldg(S.so_pk + e);
+            if (pk != 0xFFFFu) acc += gP[pk];
+            gOff[e] = acc;
+        }
+    };
     if constexpr (!SM) {
         if (crank != 0) {
             // ---- helper CTA: serve the leader's passes until it says exit.  Two cluster barriers per pass: "operation published"
@@ -556,6 +587,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                 const bool hinfo = lctl[2] != 0, hq = B.q != nullptr;
                 const size_t hmu = (size_t)hb * mu, hnp = (size_t)hb * np;
                 if (op == OP_RHS) rhs_share(B.x_state + hnp, hq ? B.qs + hnp : nullptr, lRHS, hq);
+                else if (op == OP_ASSEMBLE) assemble_share();
                 else update_share(B.x_state + hnp, B.z_state + hmu, B.y_state + hmu, B.dyg + hmu, B.dxg + hnp, lRHS, hinfo, hq);
                 csync();
             }
@@ -878,36 +910,12 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                     }
                 }
                 __syncthreads();
-                {
-                    const int dpb = bs * (bs + 1) / 2, ndiag = T * dpb;
-                    for (int e = tid; e < ndiag; e += kST) {
-                        double acc = 0.0;
-                        const uint32_t q1 = __ldg(S.sd_ptr + e + 1);
-                        for (uint32_t q = __ldg(S.sd_ptr + e); q < q1; ++q) {
-                            const gomp::Contrib cn = S.sd_con[q];
-                            acc += gRho[cn.row] * gA[cn.k1] * gA[cn.k2];
-                        }
-                        const uint16_t pk = __ldg(S.sd_pk + e);
-                        if (pk != 0xFFFFu) acc += gP[pk];
-                        const int kind = __ldg(S.sd_kind + e);
-                        if (kind == 1) acc += st.sigma;
-                        else if (kind == 2) acc = 1.0;
-                        const int t = e / dpb, rc = __ldg(S.tri_rc + (e - t * dpb)), rw = rc >> 8, c = rc & 0xFF;
-                        gDinv[(size_t)t * bb + rw * bs + c] = acc;
-                        gDinv[(size_t)t * bb + c * bs + rw] = acc;
-                    }
-                    for (int e = tid; e < S.noff; e += kST) {
-                        double acc = 0.0;
-                        const uint32_t q1 = __ldg(S.so_ptr + e + 1);
-                        for (uint32_t q = __ldg(S.so_ptr + e); q < q1; ++q) {
-                            const gomp::Contrib cn = S.so_con[q];
-                            acc += gRho[cn.row] * gA[cn.k1] * gA[cn.k2];
-                        }
-                        const uint16_t pk = __ldg(S.so_pk + e);
-                        if (pk != 0xFFFFu) acc += gP[pk];
-                        gOff[e] = acc;
-                    }
+                if (cs > 1) {
+                    if (tid == 0) sCtl[0] = OP_ASSEMBLE;
+                    csync(); // (rho per row is in the workspace: the __syncthreads above, then the cluster barrier)
                 }
+                assemble_share();
+                if (cs > 1) csync();
                 __syncthreads();
                 SMARK(PH_ASSEMBLE);
                 if (NT < 2 * kGroup) {
@@ -1562,56 +1570,63 @@ __global__ void __launch_bounds__(kStreamThreads, 1) gomp_ruiz_cluster_kernel(co
             }
         }
         csync();
-        auto pf_absmax = [&](int p) {
-            double nrm = 0.0;
-            for (int k = __ldg(S.pf_ptr + p), k1 = __ldg(S.pf_ptr + p + 1); k < k1; ++k) nrm = fmax(nrm, fabs(__ldcg(P + (__ldg(S.pf_csr + k) & 0xFFFFu))));
-            return nrm;
-        };
         double cscale = 1.0;
 #pragma unroll 1
         for (int it = 0; it < st.scaling; ++it) {
-            // ---- norms of the KKT columns: variables (P and A columns), constraints (A rows)
-            for (int p = gt; p < np; p += GT) {
-                const uint32_t rg = __ldg(S.col_range + p);
-                double na = 0.0;
-                for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) na = fmax(na, fabs(__ldcg(A + k)));
-                __stcg(dt + p, 1.0 / sqrt(limit_scaling(fmax(pf_absmax(p), na))));
+            // ---- norms of the KKT columns: variables (P and A columns), constraints (A rows); two at a time on the ELL views,
+            // as the in-kernel phase does (these loops are L2-latency bound: independent loads first)
+            for (int p = gt; p < np; p += 2 * GT) {
+                const bool two = p + GT < np;
+                const int p2 = two ? p + GT : p;
+                double na, nb_;
+                col_absmax2(S, X, p, p2, A, na, nb_);
+                const double pa = pf_absmax_g(S, p, P), pb = pf_absmax_g(S, p2, P);
+                dt[p] = 1.0 / sqrt(limit_scaling(fmax(pa, na)));
+                if (two) dt[p2] = 1.0 / sqrt(limit_scaling(fmax(pb, nb_)));
             }
-            for (int i = gt; i < mu; i += GT) {
-                const uint32_t rg = __ldg(S.row_range + i);
-                double na = 0.0;
-                for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) na = fmax(na, fabs(__ldcg(A + (__ldg(S.row_csr + k) & 0xFFFFu))));
-                __stcg(et + i, 1.0 / sqrt(limit_scaling(na)));
+            for (int i = gt; i < mu; i += 2 * GT) {
+                const bool two = i + GT < mu;
+                const int i2 = two ? i + GT : i;
+                double na, nb_;
+                row_absmax_ell2(X, mu, i, i2, A, na, nb_);
+                et[i] = 1.0 / sqrt(limit_scaling(na));
+                if (two) et[i2] = 1.0 / sqrt(limit_scaling(nb_));
             }
             csync();
             // ---- rows of A and E by the row factors, P by the column factors on both sides
-            for (int i = gt; i < mu; i += GT) {
-                const uint32_t rg = __ldg(S.row_range + i);
-                const double ea = __ldcg(et + i);
-                for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) {
-                    double *a = A + (__ldg(S.row_csr + k) & 0xFFFFu);
-                    __stcg(a, __ldcg(a) * ea);
-                }
-                __stcg(E + i, __ldcg(E + i) * ea);
+            for (int i = gt; i < mu; i += 2 * GT) {
+                const bool two = i + GT < mu;
+                const int i2 = two ? i + GT : i;
+                const double ea = et[i], eb = et[i2];
+                row_scale_ell2(X, mu, i, i2, two, A, ea, eb);
+                E[i] *= ea;
+                if (two) E[i2] *= eb;
             }
+#pragma unroll 4
             for (int k = gt; k < S.nnzPu; k += GT) {
                 const uint32_t ij = __ldg(S.Pu_ij + k);
-                __stcg(P + k, (__ldcg(P + k) * __ldcg(dt + (ij >> 16))) * __ldcg(dt + (ij & 0xFFFFu)));
+                P[k] = (P[k] * dt[ij >> 16]) * dt[ij & 0xFFFFu];
             }
             csync();
             // ---- columns of A, D and q by the column factors; cost normalisation from the scaled P
             double psum = 0.0, qn = 0.0;
-            for (int p = gt; p < np; p += GT) {
-                const uint32_t rg = __ldg(S.col_range + p);
-                const double da = __ldcg(dt + p);
-                for (int k = (int)(rg >> 8), k1 = k + (int)(rg & 0xFFu); k < k1; ++k) __stcg(A + k, __ldcg(A + k) * da);
-                __stcg(D + p, __ldcg(D + p) * da);
+            for (int p = gt; p < np; p += 2 * GT) {
+                const bool two = p + GT < np;
+                const int p2 = two ? p + GT : p;
+                const double da = dt[p], db = dt[p2];
+                col_scale2(S, X, p, p2, two, A, da, db);
+                D[p] *= da;
+                if (two) D[p2] *= db;
                 if (hasq) {
-                    const double qv = __ldcg(q + p) * da;
-                    __stcg(q + p, qv);
-                    qn = fmax(qn, fabs(qv));
+                    q[p] *= da;
+                    qn = fmax(qn, fabs(q[p]));
+                    if (two) {
+                        q[p2] *= db;
+                        qn = fmax(qn, fabs(q[p2]));
+                    }
                 }
-                psum += pf_absmax(p);
+                psum += pf_absmax_g(S, p, P);
+                if (two) psum += pf_absmax_g(S, p2, P);
             }
             psum = block_sum<kStreamThreads>(psum, sRed, tid);
             {
@@ -1620,27 +1635,28 @@ __global__ void __launch_bounds__(kStreamThreads, 1) gomp_ruiz_cluster_kernel(co
                 qn = qv[0];
             }
             if (tid == 0) {
-                __stcg(red + rank, psum);
-                __stcg(red + 16 + rank, qn);
+                red[rank] = psum;
+                red[16 + rank] = qn;
             }
             csync();
             double ps = 0.0, qm = 0.0;
             for (int r = 0; r < nb; ++r) {
-                ps += __ldcg(red + r);
-                qm = fmax(qm, __ldcg(red + 16 + r));
+                ps += red[r];
+                qm = fmax(qm, red[16 + r]);
             }
             double ct = fmax(ps / (double)S.n, limit_scaling(qm));
             ct = 1.0 / limit_scaling(ct);
-            for (int k = gt; k < S.nnzPu; k += GT) __stcg(P + k, __ldcg(P + k) * ct);
+#pragma unroll 4
+            for (int k = gt; k < S.nnzPu; k += GT) P[k] *= ct;
             if (hasq)
-                for (int p = gt; p < np; p += GT) __stcg(q + p, __ldcg(q + p) * ct);
+                for (int p = gt; p < np; p += GT) q[p] *= ct;
             cscale *= ct;
             csync();
         }
         for (int i = gt; i < mu; i += GT) {
-            const double e = __ldcg(E + i);
-            __stcg(Lo + i, __ldcg(Lo + i) * e);
-            __stcg(Hi + i, __ldcg(Hi + i) * e);
+            const double e = E[i];
+            Lo[i] *= e;
+            Hi[i] *= e;
         }
         if (gt == 0) __stcg(pre + X.pC, cscale);
         csync(); // (the next QP of this cluster reuses nothing, but keeps the CTAs of the cluster in step)
@@ -1680,6 +1696,25 @@ cudaError_t prepare_stream(int bs, bool small, size_t smem_bytes, int *ctas_per_
     PREP((gomp_admm_stream_kernel<0, kStreamThreads, false>), kStreamThreads)
 #undef PREP
 }
+// how many clusters of `cluster_size` CTAs of the 512-thread ADMM kernel the device holds at once (GPC boundaries: fewer than
+// SMs / cluster_size)
+cudaError_t stream_max_clusters(int bs, int cluster_size, size_t smem_bytes, int *n) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cluster_size, 1, 1);
+    cfg.blockDim = dim3(kStreamThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (bs == 14) return cudaOccupancyMaxActiveClusters(n, gomp_admm_stream_kernel<14, kStreamThreads, false>, &cfg);
+    if (bs == 12) return cudaOccupancyMaxActiveClusters(n, gomp_admm_stream_kernel<12, kStreamThreads, false>, &cfg);
+    return cudaOccupancyMaxActiveClusters(n, gomp_admm_stream_kernel<0, kStreamThreads, false>, &cfg);
+}
+
 cudaError_t launch_stream(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int grid, int cluster_size,
                           size_t smem_bytes, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};

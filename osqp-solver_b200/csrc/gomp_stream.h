@@ -44,6 +44,7 @@ cudaError_t prepare_stream(int bs, bool small, size_t smem_bytes, int *ctas_per_
 // grid CTAs in clusters of `cluster_size` (1: plain launch; > 1: one QP per cluster, 512-thread kernels only)
 cudaError_t launch_stream(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int grid, int cluster_size,
                           size_t smem_bytes, cudaStream_t stream);
+cudaError_t stream_max_clusters(int bs, int cluster_size, size_t smem_bytes, int *n);
 // the cluster kernel: `clusters` clusters of `cluster_size` CTAs (1, 2, 4 or 8), QPs dealt round-robin to the clusters
 cudaError_t launch_prescale(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevStream &X, int clusters, int cluster_size,
                             cudaStream_t stream);
