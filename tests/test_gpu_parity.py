@@ -427,3 +427,54 @@ def test_active_mask_freezes_problems(env):
     assert (third["iters"][off] > 0).all()
     s.close()
     ref.close()
+
+
+def test_full_batch_kkt_properties():
+    """BASELINE configs[1] at its full size (4096 QPs, more than the oracle is asked to solve in a test) through properties that
+    do not need the oracle: every QP reported optimal satisfies OSQP's own termination criteria, evaluated here from the
+    returned x and y in plain numpy (primal residual dist(Ax, [l, u]) and dual residual |Px + A'y| against eps_abs + eps_rel x
+    the norms OSQP uses, dual signs on inactive sides); every primal infeasible one comes with a certificate that proves it;
+    a random sample of 96 is compared with the oracle on top."""
+    pkg, O = package(), oracle()
+    P = pkg.problem
+    pat = P.Pattern(P.default_config())
+    B = 4096
+    d = P.generate(pat, 0, B)
+    s = make_solver(pkg, pat, d, settings=pkg.solver.default_settings(linsys=4))   # the kernel bench.py measures
+    assert s.info()["linsys"] == 4
+    s.set_warm_start(d["x0"])
+    got = s.solve(want_y=True)
+    cert, _ = s.certificates()
+    s.close()
+    Pm = pat.P_scipy()
+    eps = 1e-3
+    n_opt = n_inf = 0
+    for b in range(B):
+        A = pat.A_scipy(d["A_val"][b])
+        l, u = np.maximum(d["l"][b], -1e30), np.minimum(d["u"][b], 1e30)
+        code = got["exit_code"][b]
+        if code in (0, 3):
+            x, y = got["x"][b], got["y"][b]
+            ax, px, aty = A @ x, Pm @ x, A.T @ y
+            z = np.clip(ax, l, u)
+            slack = 10.0 if code == 3 else 1.0   # kOptimalInaccurate: the 10x tolerances of the max_iter check
+            # (the unscaled criteria of OSQP; its z is not returned, so dist(Ax, [l, u]) <= |Ax - z_osqp| is the testable form)
+            assert np.abs(ax - z).max() <= slack * (eps + eps * max(np.abs(ax).max(), np.abs(z).max())) * 1.0001, b
+            assert np.abs(px + aty).max() <= slack * (eps + eps * max(np.abs(px).max(), np.abs(aty).max())) * 1.0001, b
+            # dual signs: y <= 0 only where the lower bound can be active, y >= 0 only where the upper one can
+            tol = slack * 1e-2 * max(1.0, np.abs(y).max())
+            assert (y[u > 1e29] <= tol).all() and (y[l < -1e29] >= -tol).all(), b
+            n_opt += 1
+        elif code in (1, 4):
+            v = cert[b]
+            assert np.isnan(got["x"][b]).all() and abs(np.abs(v).max() - 1.0) < 1e-12
+            support = u @ np.maximum(v, 0.0) + l @ np.minimum(v, 0.0)
+            assert support < 0 and np.abs(A.T @ v).max() <= 1e-3 * max(1.0, abs(support)), b
+            n_inf += 1
+        else:
+            raise AssertionError((b, code))
+    assert n_opt > 0.95 * B and n_inf > 0
+    pick = np.random.default_rng(0).choice(B, 96, replace=False)
+    sub = {k: v[pick] for k, v in d.items()}
+    ref = oracle_batch(O, pat, sub)
+    compare({k: got[k][pick] for k in ("x", "y", "exit_code", "iters", "rho_updates")}, ref)
