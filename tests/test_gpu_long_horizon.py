@@ -249,3 +249,53 @@ def test_reference_example_shape_n6_w802():
         assert got2["exit_code"][b] == ref.exit_code and got2["iters"][b] == ref.iter
         if ref.exit_code == 0:
             assert np.abs(got2["x"][b] - ref.x).max() < REL_TOL * np.abs(ref.x).max()
+
+
+def test_cluster_mode_matches_single_cta_and_is_repeatable(monkeypatch):
+    """Long horizons, small batch: the QP is served by a thread-block cluster (Ruiz cluster kernel + leader / helper CTAs over
+    distributed shared memory).  Against the single-CTA path on the same inputs: same status, iterations and rho
+    updates, x / y to 1e-9 (only the cost normalisation's sum is ordered differently); repeated solves are bit-identical (no
+    race between the cluster's CTAs); an update round works through the cluster path; all of it equals the oracle."""
+    pkg, O = package(), oracle()
+    P = pkg.problem
+    pat = P.Pattern(P.default_config(waypoints=200))
+    d = P.generate(pat, 40, 6)
+
+    def run(cluster):
+        if cluster is None:
+            monkeypatch.delenv("GOMP_RUIZ_CLUSTER", raising=False)
+        else:
+            monkeypatch.setenv("GOMP_RUIZ_CLUSTER", str(cluster))
+        s = make_solver(pkg, pat, d)
+        info = s.info()
+        assert info["linsys"] == GLOBAL
+        outs = []
+        for _ in range(3):
+            s.setup(d["A_val"], d["l"], d["u"])
+            s.set_warm_start(d["x0"])
+            outs.append(s.solve(want_y=True))
+        ok = outs[0]["exit_code"] == 0
+        x = np.where(ok[:, None], outs[0]["x"], d["x0"])
+        upd = P.relinearize(pat, 40, x)
+        s.update(upd["A_val"], upd["l"], upd["u"])
+        second = s.solve(want_y=True)
+        s.close()
+        return info, outs, second
+
+    info_c, outs_c, second_c = run(None)        # AUTO: 6 QPs leave SMs idle -> clusters of 8
+    assert info_c["grid"] == 6 * 8
+    info_1, outs_1, second_1 = run(0)           # one CTA per QP, Ruiz inside the ADMM kernel
+    assert info_1["grid"] == 6
+    for k in ("x", "y", "exit_code", "iters", "rho_updates"):
+        np.testing.assert_array_equal(outs_c[0][k], outs_c[1][k])
+        np.testing.assert_array_equal(outs_c[0][k], outs_c[2][k])
+    for a, b in ((outs_c[0], outs_1[0]), (second_c, second_1)):
+        for k in ("exit_code", "iters", "rho_updates"):
+            np.testing.assert_array_equal(a[k], b[k])
+        ok = a["exit_code"] == 0
+        np.testing.assert_allclose(a["x"][ok], b["x"][ok], rtol=0, atol=1e-9 * np.abs(b["x"][ok]).max())
+    compare(outs_c[0], oracle_batch(O, pat, d))
+    for cs in (2, 4):                           # forced smaller clusters
+        _, outs, _ = run(cs)
+        for k in ("exit_code", "iters", "rho_updates"):
+            np.testing.assert_array_equal(outs[0][k], outs_1[0][k])
