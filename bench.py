@@ -380,7 +380,7 @@ def extra_sqp_sequence(pkg, O, torch, batch=4096, rounds=10, cpu_sample=64):
             "all_rounds_status_agreement": float(code_eq), "all_rounds_iterations_agreement": float(iter_eq)}
 
 
-def extra_long_horizon(pkg, O, W=400, batches=(1, 148), cpu_sample=16, name="BASELINE.json configs[3]", **cfg_kw):
+def extra_long_horizon(pkg, O, W=400, batches=(1, 32, 148), cpu_sample=16, name="BASELINE.json configs[3]", **cfg_kw):
     """BASELINE.json configs[3]: N=7, H=400 on the streamed back end, batch 1 and one QP per SM, beside the oracle (also used for
     configs[0], the reference example's shape: N=6, W=802, two balls, no obstacle lines)."""
     P, S = pkg.problem, pkg.solver
@@ -401,6 +401,8 @@ def extra_long_horizon(pkg, O, W=400, batches=(1, 148), cpu_sample=16, name="BAS
             best = min(best, s.info()["last_solve_ms"])
         out[f"ms_b{batch}"] = best
         out[f"qps_b{batch}"] = batch / best * 1e3
+        out[f"ctas_per_qp_b{batch}"] = s.info()["grid"] // min(batch, s.info()["grid"])  # > 1: a thread-block cluster per QP
+        out[f"iters_max_b{batch}"] = int(results["iters"].max())
         out["linsys"] = s.info()["linsys"]
         s.close()
     n_cpu = min(cpu_sample, nmax)
