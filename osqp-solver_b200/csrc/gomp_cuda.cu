@@ -931,6 +931,9 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
             if (const char *e = std::getenv("GOMP_RUIZ_CLUSTER")) {
                 const int v = std::atoi(e);
                 cs = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0;
+                int fit = 0; // a forced size: as many clusters as are co-resident, the leaders then take several QPs each
+                h->max_clusters = (cs > 0 && stream_max_clusters(s.bs, cs, h->smem_bytes, &fit) == cudaSuccess) ? fit : 0;
+                cudaGetLastError();
             }
             h->pre_cluster = cs;
         }

@@ -299,3 +299,21 @@ def test_cluster_mode_matches_single_cta_and_is_repeatable(monkeypatch):
         _, outs, _ = run(cs)
         for k in ("exit_code", "iters", "rho_updates"):
             np.testing.assert_array_equal(outs[0][k], outs_1[0][k])
+
+
+def test_cluster_mode_more_problems_than_clusters(monkeypatch):
+    """Forced clusters of 8 with more QPs (40) than clusters of that size are co-resident (14-16 on a B200: a cluster lives inside
+    one GPC): leaders pull several QPs from the work queue one after the other, the helpers follow through the control words;
+    oracle parity."""
+    pkg, O = package(), oracle()
+    P = pkg.problem
+    pat = P.Pattern(P.default_config(waypoints=100))
+    d = P.generate(pat, 700, 40)
+    monkeypatch.setenv("GOMP_RUIZ_CLUSTER", "8")
+    s = make_solver(pkg, pat, d, settings=pkg.solver.default_settings(linsys=GLOBAL))
+    grid = s.info()["grid"]
+    assert grid % 8 == 0 and 8 <= grid // 8 < 40, grid
+    s.set_warm_start(d["x0"])
+    got = s.solve(want_y=True)
+    s.close()
+    compare(got, oracle_batch(O, pat, d))
