@@ -892,6 +892,12 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
         if (h->d_row_ell.upload(s.row_ent) != cudaSuccess || h->d_col_ell.upload(s.col_row) != cudaSuccess)
             return bail(fail(GOMP_ERR_ALLOC, "cudaMalloc failed for the ELL pattern views"));
         x.row_ell = h->d_row_ell.p; x.col_ell = h->d_col_ell.p; x.roww = s.roww; x.colw = s.colw;
+        for (int k = 0; k < 256; ++k) x.rlen_blk[k] = 0;
+        for (int i = 0; i < s.m_used; ++i) {
+            const int k = std::min(i >> 8, 255);
+            x.rlen_blk[k] = (unsigned char)std::max<int>(x.rlen_blk[k], (int)(s.row_range[(size_t)i] & 0xFFu));
+        }
+        for (int k = 254; k >= 0; --k) x.rlen_blk[k] = std::max(x.rlen_blk[k], x.rlen_blk[k + 1]); // (monotone even if the order were not)
     }
     h->ctas_per_sm = occ;
     h->grid = (int)std::min<int64_t>(batch, (int64_t)h->num_sms * occ);

@@ -116,8 +116,13 @@ __device__ __forceinline__ double pf_dot_g(const DevSym &S, int p, const double 
 // has up to 8 independent L2 loads in flight per level instead of one (these loops are L2-latency bound).
 // Summation order per row / column is the CSR / CSC order, i.e. the results equal the *_g versions bit for bit.
 constexpr uint32_t kNone = 0xFFFFFFFFu;
+// Rows are stored longest first (symbolic.h sorts the non-empty rows by entry count), so the longest row of the 256-row block
+// the smaller index of a pair falls into bounds both rows: the loops stop there instead of walking the full ELL width (most
+// GOMP rows hold one to three entries, the Cartesian ones 2N) -- fewer index words fetched from L2, same entries in the same
+// order.  Columns: their lengths are in the range words the loop reads anyway.
+__device__ __forceinline__ int ell_row_width(const DevStream &X, int i) { return (int)X.rlen_blk[(i >> 8) < 255 ? (i >> 8) : 255]; }
 #define ELL_ROW2(i1, i2, ...)                                                               \
-    _Pragma("unroll 4") for (int j__ = 0; j__ < X.roww; ++j__) {                            \
+    _Pragma("unroll 4") for (int j__ = 0, w__ = ell_row_width(X, (i1) < (i2) ? (i1) : (i2)); j__ < w__; ++j__) { \
         const uint32_t e1 = __ldg(X.row_ell + (size_t)j__ * mu + (i1));                     \
         const uint32_t e2 = __ldg(X.row_ell + (size_t)j__ * mu + (i2));                     \
         const bool h1 = e1 != kNone, h2 = e2 != kNone;                                      \
@@ -159,7 +164,7 @@ __device__ __forceinline__ void row_scale_ell2(const DevStream &X, int mu, int i
 #define ELL_COL2(p1, p2, ...)                                                               \
     const uint32_t rg1 = __ldg(S.col_range + (p1)), rg2 = __ldg(S.col_range + (p2));       \
     const int s1__ = (int)(rg1 >> 8), n1__ = (int)(rg1 & 0xFFu), s2__ = (int)(rg2 >> 8), n2__ = (int)(rg2 & 0xFFu); \
-    _Pragma("unroll 4") for (int j__ = 0; j__ < X.colw; ++j__) {                            \
+    _Pragma("unroll 4") for (int j__ = 0, w__ = n1__ > n2__ ? n1__ : n2__; j__ < w__; ++j__) { \
         const bool h1 = j__ < n1__, h2 = j__ < n2__;                                        \
         const int k1 = h1 ? s1__ + j__ : 0, k2 = h2 ? s2__ + j__ : 0;                        \
         __VA_ARGS__                                                                         \

@@ -25,6 +25,7 @@ struct DevStream {
     const uint32_t *row_ell; // [roww][m_used] (pos << 16 | value index), 0xFFFFFFFF = none
     const uint16_t *col_ell; // [colw][n_pad] compact row of the j-th entry of a column
     int roww, colw;
+    unsigned char rlen_blk[256]; // longest row of rows [256 k, 256 k + 256) of the compact (longest-first) row order; block 255 covers the rest
     int gen_ring;      // generic path: ring slots (one stage each) per substitution warp, <= kStreamRing
     int grp, grp_ring; // fast path: stages per bulk copy, groups in flight per substitution warp
     int e_scratch;     // ... and the row factors E behind them (offset into the ring in doubles, 0 = they stay in the workspace)
