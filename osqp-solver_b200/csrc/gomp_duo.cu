@@ -465,7 +465,11 @@ __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("
 template <bool ROWS, int N, int G0 = 0, class F>
 __device__ __forceinline__ void duo_ell_lines(const DevDuo &X, uint32_t mine, uint32_t pad, F &&f) {
     if constexpr (G0 < N) {
-        constexpr int G = (N - G0) < 4 ? (N - G0) : 4;
+        // Groups of 2, 3, then 4 slots: the slots hold rows / columns longest first, so the lengths differ most among the first
+        // ones (GOMP, N = 7: rows 7 7 3 2 2 1 1 1 1, columns 7 7 4 4) -- a group pads every slot to its longest, and groups of
+        // four would walk 37 row entries and 28 column entries per thread where 27 and 22 carry values.
+        constexpr int GW = G0 == 0 ? 2 : (G0 == 2 ? 3 : 4);
+        constexpr int G = (N - G0) < GW ? (N - G0) : GW;
         int maxlen = 0;
 #pragma unroll
         for (int g = 0; g < G; ++g) maxlen = max(maxlen, ROWS ? X.rlen[G0 + g] : X.clen[G0 + g]);
@@ -480,7 +484,7 @@ __device__ __forceinline__ void duo_ell_lines(const DevDuo &X, uint32_t mine, ui
             }
             f(std::integral_constant<int, G0>{}, e);
         }
-        duo_ell_lines<ROWS, N, G0 + 4>(X, mine, pad, f);
+        duo_ell_lines<ROWS, N, G0 + G>(X, mine, pad, f);
     }
 }
 // acc[slot] += sum over the slot's entries of value * vec[operand]   (values at aVal, operand vector at aVec)
