@@ -31,6 +31,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -67,23 +69,121 @@ int fail(int code, const std::string &msg) {
 // ================================================================================================
 //                                           host side
 // ================================================================================================
+// Device allocations of the handles go through a small per-process cache of freed blocks (per device, keyed by rounded size):
+// a planner in the reference's style builds and drops a QPSolver per horizon (src/gomp-solver.h:61-65, ten per plan), and
+// cudaMalloc / cudaFree stalls of up to 100 ms each dominated such a plan (5 ms per solve, 14 ms per handle otherwise).  A handle
+// waits for its stream before it releases anything, so a cached block is idle.  Blocks above the cap go back to the driver.
+class DevCache {
+public:
+    static DevCache &get() {
+        static DevCache c;
+        return c;
+    }
+    cudaError_t alloc(void **p, size_t bytes) {
+        const size_t sz = rounded(bytes);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            auto it = free_.find({dev, sz});
+            if (it != free_.end() && !it->second.empty()) {
+                *p = it->second.back();
+                it->second.pop_back();
+                cached_ -= sz;
+                live_[*p] = {dev, sz};
+                return cudaSuccess;
+            }
+        }
+        cudaError_t e = cudaMalloc(p, sz);
+        if (e != cudaSuccess) { // memory held by the cache may be what is missing: give it back and retry once
+            cudaGetLastError();
+            trim(0);
+            e = cudaMalloc(p, sz);
+        }
+        if (e == cudaSuccess) {
+            std::lock_guard<std::mutex> lock(mu_);
+            live_[*p] = {dev, sz};
+        }
+        return e;
+    }
+    void release(void *p) {
+        if (!p) return;
+        std::pair<int, size_t> key;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            auto it = live_.find(p);
+            if (it == live_.end()) { // not ours
+                cudaFree(p);
+                return;
+            }
+            key = it->second;
+            live_.erase(it);
+            if (cached_ + key.second <= kCap) {
+                free_[key].push_back(p);
+                cached_ += key.second;
+                return;
+            }
+        }
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != key.first) cudaSetDevice(key.first);
+        cudaFree(p);
+        if (cur != key.first) cudaSetDevice(cur);
+    }
+    void trim(size_t keep) {
+        std::vector<std::pair<int, void *>> drop;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            for (auto &kv : free_)
+                while (!kv.second.empty() && cached_ > keep) {
+                    drop.push_back({kv.first.first, kv.second.back()});
+                    kv.second.pop_back();
+                    cached_ -= kv.first.second;
+                }
+        }
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto &d : drop) {
+            cudaSetDevice(d.first);
+            cudaFree(d.second);
+        }
+        cudaSetDevice(cur);
+    }
+
+private:
+    static constexpr size_t kCap = (size_t)2 << 30; // bytes kept for reuse per process
+    static size_t rounded(size_t bytes) {
+        bytes = std::max<size_t>(bytes, 256);
+        if (bytes <= ((size_t)1 << 20)) { // next power of two
+            size_t s = 256;
+            while (s < bytes) s <<= 1;
+            return s;
+        }
+        return (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1); // whole MiB
+    }
+    std::mutex mu_;
+    std::map<std::pair<int, size_t>, std::vector<void *>> free_;
+    std::map<void *, std::pair<int, size_t>> live_;
+    size_t cached_ = 0;
+};
+
 template <typename T>
 struct DevArray {
     T *p = nullptr;
     size_t count = 0;
     cudaError_t upload(const std::vector<T> &h) {
         count = h.size();
-        cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+        cudaError_t e = DevCache::get().alloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
         if (e != cudaSuccess) return e;
         if (count) e = cudaMemcpy(p, h.data(), count * sizeof(T), cudaMemcpyHostToDevice);
         return e;
     }
     cudaError_t alloc(size_t n) {
         count = n;
-        return cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T));
+        return DevCache::get().alloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) DevCache::get().release(p);
         p = nullptr;
     }
 };

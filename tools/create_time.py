@@ -7,4 +7,4 @@ def mk():
 s=mk(); s.set_warm_start(d["x0"]); s.solve(); s.close()
 for rep in range(4):
     t0=time.perf_counter(); s=mk(); t1=time.perf_counter(); s.set_warm_start(d["x0"]); s.solve(); t2=time.perf_counter(); s.solve(); t3=time.perf_counter(); s.close(); t4=time.perf_counter()
-    print(os.environ.get("GOMP_RUIZ_CLUSTER","auto"), "create %.1f ms, first solve %.1f ms, second solve %.1f ms, destroy %.1f ms" % ((t1-t0)*1e3,(t2-t1)*1e3,(t3-t2)*1e3,(t4-t3)*1e3, 0))
+    print(os.environ.get("GOMP_RUIZ_CLUSTER","auto"), "create %.1f ms, first solve %.1f ms, second solve %.1f ms, destroy %.1f ms" % ((t1-t0)*1e3,(t2-t1)*1e3,(t3-t2)*1e3,(t4-t3)*1e3))
