@@ -32,6 +32,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -797,10 +798,51 @@ int gomp_batch_create(gomp_batch **out, const gomp_settings *settings, int64_t b
     h->st = st;
     h->batch = batch;
     h->no_predict = std::getenv("GOMP_NO_PREDICT_ORDER") != nullptr;
-    if (!gomp::analyse(h->sym, n, m, P_colptr, P_rowidx, P_val, A_colptr, A_rowidx, st.var_order, st.block_size)) {
-        std::string msg = h->sym.error;
-        delete h;
-        return fail(GOMP_ERR_UNSUPPORTED, msg);
+    // The symbolic analysis depends on the structure only (patterns of P and A, P's values, the variable order): a planner that
+    // builds a QPSolver per horizon and plans again and again (the reference's time-shrink loop, ten horizons per plan) meets the
+    // same structures every time, so finished analyses are kept per process, keyed by a hash of everything they were computed from.
+    {
+        const int64_t nnzP = P_colptr[n], nnzA_ = A_colptr[n];
+        uint64_t key = 1469598103934665603ull;
+        auto mix = [&key](const void *ptr, size_t bytes) {
+            const unsigned char *c = static_cast<const unsigned char *>(ptr);
+            size_t k = 0;
+            for (; k + 8 <= bytes; k += 8) {
+                uint64_t w;
+                std::memcpy(&w, c + k, 8);
+                key = (key ^ w) * 1099511628211ull;
+                key ^= key >> 29;
+            }
+            for (; k < bytes; ++k) key = (key ^ c[k]) * 1099511628211ull;
+        };
+        const int64_t dims[5] = {n, m, nnzP, nnzA_, (int64_t)st.block_size};
+        mix(dims, sizeof dims);
+        mix(P_colptr, (size_t)(n + 1) * 8);
+        if (P_rowidx) mix(P_rowidx, (size_t)nnzP * 8);
+        if (P_val) mix(P_val, (size_t)nnzP * 8);
+        mix(A_colptr, (size_t)(n + 1) * 8);
+        if (A_rowidx) mix(A_rowidx, (size_t)nnzA_ * 8);
+        if (st.var_order) mix(st.var_order, (size_t)n * 8);
+        static std::mutex sym_mu;
+        static std::map<uint64_t, std::shared_ptr<const gomp::Symbolic>> sym_cache;
+        std::shared_ptr<const gomp::Symbolic> hit;
+        {
+            std::lock_guard<std::mutex> lock(sym_mu);
+            auto it = sym_cache.find(key);
+            if (it != sym_cache.end() && it->second->n == n && it->second->m == m && it->second->nnzA == nnzA_) hit = it->second;
+        }
+        if (hit && !std::getenv("GOMP_NO_SYMBOLIC_CACHE")) {
+            h->sym = *hit;
+        } else {
+            if (!gomp::analyse(h->sym, n, m, P_colptr, P_rowidx, P_val, A_colptr, A_rowidx, st.var_order, st.block_size)) {
+                std::string msg = h->sym.error;
+                delete h;
+                return fail(GOMP_ERR_UNSUPPORTED, msg);
+            }
+            std::lock_guard<std::mutex> lock(sym_mu);
+            if (sym_cache.size() >= 64) sym_cache.clear();
+            sym_cache[key] = std::make_shared<const gomp::Symbolic>(h->sym);
+        }
     }
     int rc = GOMP_OK;
     auto bail = [&](int code) {
