@@ -97,7 +97,23 @@ class ClockSampler:
 # start + solve.  The timed region ends with the drain of the last batches (their max_iter QPs take 70 ms each), so
 # few steps under-report the steady state: 32 steps 197 k, 128 steps 213 k on one build; 64 -> 233 k, 256 -> 241 k now.
 PIPE = int(os.environ.get("GOMP_BENCH_PIPE", "12"))
-GATHER = os.environ.get("GOMP_BENCH_GATHER", "1") != "0"  # A/B switch: the per-step NCCL gather of the multi-GPU runs
+# SMs shared between the batches in flight (gomp_batch_set_max_ctas, include/gomp_cuda.h): a batch's persistent CTAs hold their
+# SMs until its work queue is empty, so with one CTA per SM the batches run one after the other and each ends with its two
+# max_iter QPs (~45 ms) alone on their SMs.  LANES batches co-resident on num_sms / LANES CTAs each last longer than their
+# longest solve, and the stragglers of one overlap with the bulk of the others.  Measured on B200 (20 / 96 steps, `value`):
+# LANES 1: 286 k / 315 k, 2: 292 k / 327 k, 3: 297 k / 333 k, 4: 307 k / 337 k, 5: 295 k / 338 k, 6: 303 k / 341 k, 8: 297 k /
+# 321 k, 12: 291 k / 260 k QP/s (a handle's next batch waits for its previous one: lanes need PIPE > LANES handles).
+# Host-buffer leg (`e2e`): its batches become ready one H2D copy (6 ms) apart and the host submits a batch only after it has
+# collected the one PIPE steps before, so the pipeline knows its depth: the first batches (fewer than LANES in flight) and the
+# last ones (fewer than LANES to come) get the wider share -- 20 steps: 268 k without, 281 k with that ramp.  The device-
+# resident leg enqueues every step before the first one has finished; there the ramp only delays the lanes (307 k -> 301 k).
+LANES = int(os.environ.get("GOMP_BENCH_LANES", "4"))
+
+
+def lane_ctas(k, nsteps, num_sms, ramp):
+    """CTA cap of step k of a run of nsteps pipelined steps (0 = no cap); ramp bit 0: first batches, bit 1: last batches."""
+    lanes = max(1, min(LANES, k + 1 if ramp & 1 else LANES, nsteps - k if ramp & 2 else LANES))
+    return -(-num_sms // lanes) if lanes > 1 else 0
 
 
 def workload(pkg):
@@ -109,7 +125,7 @@ def workload(pkg):
                         "(eps 1e-3, adaptive_rho_interval pinned to 25)",
             "n_dim": 7, "waypoints": 50, "n": pat.n, "m": pat.m, "nnzA": pat.nnzA, "batch_per_gpu": BATCH_PER_GPU,
             "l2_policy": "inputs larger than L2 (305 MB of A_val/l/u per step vs 126 MB L2)",
-            "batches_in_flight": PIPE}
+            "batches_in_flight": PIPE, "sm_lanes": LANES}
     return cfg, pat, desc
 
 
@@ -482,8 +498,11 @@ def run_gpu(args):
     iters = np.empty(B, dtype=np.int32)
     rup = np.empty(B, dtype=np.int32)
 
-    def step_resident(k=0):
+    num_sms = solver.info()["num_sms"]
+
+    def step_resident(k=0, nsteps=1):
         sv = solvers[k % PIPE]
+        sv.set_max_ctas(lane_ctas(k, nsteps, num_sms, int(os.environ.get("GOMP_BENCH_LANE_RAMP", "0"))) if nsteps > 1 else 0)
         sv.setup(dev["A_val"], dev["l"], dev["u"])
         sv.set_warm_start(dev["x0"])
         sv.solve_async()
@@ -514,7 +533,7 @@ def run_gpu(args):
         for st_ in streams:
             st_.wait_event(ev0)
         for k in range(nsteps):
-            step_resident(k)
+            step_resident(k, nsteps)
             if world > 1 and GATHER:
                 gather_step(k)
         for st_ in streams:
@@ -574,8 +593,9 @@ def run_gpu(args):
     e2e_solvers = [make(False, streams[k]) for k in range(PIPE)]
     x_hosts = [torch.empty((B, pat.n), dtype=torch.float64).pin_memory() for _ in range(PIPE)]
 
-    def e2e_submit(k):
+    def e2e_submit(k, nsteps):
         sv = e2e_solvers[k % PIPE]
+        sv.set_max_ctas(lane_ctas(k, nsteps, num_sms, int(os.environ.get("GOMP_BENCH_E2E_LANE_RAMP", "3"))))
         sv.setup(host["A_val"], host["l"], host["u"])
         sv.set_warm_start(host["x0"])
         sv.solve_async()
@@ -587,7 +607,7 @@ def run_gpu(args):
         for k in range(nsteps):
             if k >= PIPE:
                 e2e_collect(k - PIPE)
-            e2e_submit(k)
+            e2e_submit(k, nsteps)
         for k in range(max(0, nsteps - PIPE), nsteps):
             e2e_collect(k)
 

@@ -199,6 +199,17 @@ int gomp_batch_get_certificates(gomp_batch *h, double *prim_inf_cert, double *du
  * converged or failed while others still iterate. */
 int gomp_batch_set_active(gomp_batch *h, const int32_t *active);
 
+/* Cap on the CTAs the following solves of this handle launch (0 = default: every resident slot of the device; ignored
+ * by the cluster mode of the streamed back end).  No counterpart in the reference (one QPSolver = one CPU thread); it is
+ * the knob a caller who keeps SEVERAL batches in flight on one GPU uses to share the SMs between them.  A batch's CTAs are
+ * persistent -- they leave their SM only when the batch's work queue is empty -- so with the default, batches run one
+ * after the other and each ends with its longest solves (a max_iter QP: ~45 ms on 4096 x (N=7, H=50)) alone on their SMs.
+ * With a cap of num_sms / L, L batches are co-resident, a batch lasts L times longer than its longest solve matters, and
+ * the stragglers of one batch overlap with the bulk of the others: 4096 x (N=7, H=50), 12 handles, L = 4 (37 CTAs):
+ * 315 k -> 337 k QP/s steady state.  A caller that knows its queue is running empty lifts the cap for the last batches
+ * (bench.py: L = min(4, batches already in flight + 1, batches still to come + 1)). */
+int gomp_batch_set_max_ctas(gomp_batch *h, int32_t max_ctas);
+
 /* Device-side views of a handle, for callers that keep an SQP round on the GPU without linking the CUDA runtime
  * themselves (gomp_problem.h, device section): the handle's own copies of A_val / l / u (NULL while that input is
  * borrowed from the caller), the primal results of the last solve [batch, n] and the stream all of the handle's

@@ -239,9 +239,9 @@ __global__ void peak_fp64_kernel(double *out, int iters) {
 }
 // Work-queue order for a warm re-solve: problems in descending order of the iterations their previous solve took
 // (bucketed), so that the few long solves of a batch start first instead of forming its tail.  One CTA.
-// The same kernel maps OSQP's status_val to osqp-cpp's OsqpExitCode so that results can be handed
-// to a device consumer without a host round trip.
-__device__ __forceinline__ int exit_code_of(int status) {
+// exit_code_of maps OSQP's status_val to osqp-cpp's OsqpExitCode; exit_code_kernel does so on the device so
+// that results can be handed to a device consumer without a host round trip.
+__host__ __device__ __forceinline__ int exit_code_of(int status) {
     switch (status) {
     case 1: return GOMP_EXIT_OPTIMAL;
     case 2: return GOMP_EXIT_OPTIMAL_INACCURATE;
@@ -254,10 +254,11 @@ __device__ __forceinline__ int exit_code_of(int status) {
     default: return GOMP_EXIT_UNKNOWN;
     }
 }
-__global__ void order_by_iters_kernel(const int *__restrict__ iters, const int *__restrict__ status, int n, int *__restrict__ order,
-                                      int *__restrict__ code) {
+__global__ void exit_code_kernel(const int *__restrict__ status, int n, int *__restrict__ code) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) code[b] = exit_code_of(status[b]);
+}
+__global__ void order_by_iters_kernel(const int *__restrict__ iters, int n, int *__restrict__ order) {
     __shared__ int hist[257], base[257];
-    for (int b = threadIdx.x; b < n; b += blockDim.x) code[b] = exit_code_of(status[b]);
     for (int k = threadIdx.x; k < 257; k += blockDim.x) hist[k] = 0;
     __syncthreads();
     auto bucket = [](int it) { return 255 - min(255, max(0, it) >> 4); }; // long solves -> low bucket index -> front of the queue
@@ -444,6 +445,9 @@ struct gomp_batch {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr;
+    int max_ctas = 0;        // gomp_batch_set_max_ctas: cap on the CTAs of the following solves (0 = one per resident slot)
+    bool iters_fresh = false; // d_iters / d_status hold the previous solve of the problems now loaded
+    bool code_valid = false;  // d_code holds the exit codes of the last solve
     int64_t batch = 0, launches = 0;
     double last_solve_ms = 0, last_h2d_ms = 0;
     bool has_q = false, data_loaded = false;
@@ -648,6 +652,7 @@ int load_data(gomp_batch *h, const double *A_val, const double *l, const double 
     if (cold) {
         h->pending_flags = 1;   // cold start; a pending warm start belongs to the previous problem
         h->order_valid = false; // new problems: the previous iteration counts say nothing about them
+        h->iters_fresh = false;
     }
     h->data_loaded = true;
     return GOMP_OK;
@@ -1218,41 +1223,54 @@ int gomp_batch_solve(gomp_batch *h) {
     b.status = h->d_status.p; b.iters = h->d_iters.p; b.rho_updates = h->d_rup.p;
     b.pri_res = h->d_pri.p; b.dua_res = h->d_dua.p; b.obj_val = h->d_obj.p; b.work_counter = h->d_counter.p; b.prof = h->d_prof.p; b.active = h->active_src;
     // cold solve of new problems from a primal warm start: queue order from the warm start's constraint violation (see
-    // predict_key_kernel) when the batch holds more QPs than are resident at once; GOMP_NO_PREDICT_ORDER=1 keeps index order
-    if (!h->order_valid && (h->pending_flags & 3) == 3 && h->x0_src != nullptr && h->batch > (int64_t)2 * h->num_sms * std::max(1, h->ctas_per_sm) &&
-        !h->no_predict) {
-        if (!h->d_pred.p) CUDA_TRY(h->d_pred.alloc((size_t)h->batch));
+    // predict_key_kernel) when the batch holds more QPs than are resident at once; GOMP_NO_PREDICT_ORDER=1 keeps index order.
+    // Warm re-solve of the problems of the previous solve (gomp_batch_update): queue order from their iteration counts.
+    const bool predict = !h->order_valid && (h->pending_flags & 3) == 3 && h->x0_src != nullptr &&
+                         h->batch > (int64_t)2 * h->num_sms * std::max(1, h->ctas_per_sm) && !h->no_predict;
+    const bool reorder = !h->order_valid && !predict && h->iters_fresh;
+    if (predict || reorder) {
+        if (predict && !h->d_pred.p) CUDA_TRY(h->d_pred.alloc((size_t)h->batch));
         if (!h->d_order.p) CUDA_TRY(h->d_order.alloc((size_t)h->batch));
-        if (!h->d_code.p) CUDA_TRY(h->d_code.alloc((size_t)h->batch));
-        const unsigned blocks = (unsigned)((h->batch * 32 + 255) / 256);
-        predict_key_kernel<<<blocks, 256, 0, h->stream>>>(h->ds, h->A_src, (long long)s.nnzA, h->l_src, h->u_src, h->x0_src, (int)h->batch, h->d_pred.p);
-        order_by_iters_kernel<<<1, 1024, 0, h->stream>>>(h->d_pred.p, h->d_status.p, (int)h->batch, h->d_order.p, h->d_code.p);
+        cudaStream_t ks = h->stream;
+        if (predict) {
+            const unsigned blocks = (unsigned)((h->batch * 32 + 255) / 256);
+            predict_key_kernel<<<blocks, 256, 0, ks>>>(h->ds, h->A_src, (long long)s.nnzA, h->l_src, h->u_src, h->x0_src, (int)h->batch, h->d_pred.p);
+            h->launches += 1;
+        }
+        order_by_iters_kernel<<<1, 1024, 0, ks>>>(predict ? h->d_pred.p : h->d_iters.p, (int)h->batch, h->d_order.p);
         CUDA_TRY(cudaGetLastError());
-        h->launches += 2;
+        h->launches += 1;
         h->order_valid = true;
     }
     b.order = h->order_valid ? h->d_order.p : nullptr;
     CUDA_TRY(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    if (h->duo) CUDA_TRY(launch_duo(h->dd.rpt, h->dd.cpt, s.bs, h->ds, h->db, h->dst, h->dd, h->grid, h->smem_bytes, h->stream));
+    const int grid = h->max_ctas > 0 && h->solve_cluster <= 1 ? std::min(h->grid, h->max_ctas) : h->grid;
+    if (h->duo) CUDA_TRY(launch_duo(h->dd.rpt, h->dd.cpt, s.bs, h->ds, h->db, h->dst, h->dd, grid, h->smem_bytes, h->stream));
     else if (h->streamed) {
         if (h->pre_cluster > 0) {
             const int clusters = (int)std::max<int64_t>(1, std::min<int64_t>(h->batch, h->max_clusters > 0 ? h->max_clusters : h->num_sms / h->pre_cluster));
             CUDA_TRY(launch_prescale(h->ds, h->db, h->dst, h->dx, clusters, h->pre_cluster, h->stream));
             h->launches += 1;
         }
-        CUDA_TRY(launch_stream(h->ds, h->db, h->dst, h->dx, h->grid, h->solve_cluster, h->smem_bytes, h->stream));
+        CUDA_TRY(launch_stream(h->ds, h->db, h->dst, h->dx, grid, h->solve_cluster, h->smem_bytes, h->stream));
     }
-    else CUDA_TRY(h->kernel.launch(h->ds, h->db, h->dst, h->grid, h->smem_bytes, h->stream));
+    else CUDA_TRY(h->kernel.launch(h->ds, h->db, h->dst, grid, h->smem_bytes, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
-    // queue order of the next solve, should it be a warm re-solve of the same problems (gomp_batch_update)
-    if (!h->d_order.p) CUDA_TRY(h->d_order.alloc((size_t)h->batch));
-    if (!h->d_code.p) CUDA_TRY(h->d_code.alloc((size_t)h->batch));
-    order_by_iters_kernel<<<1, 1024, 0, h->stream>>>(h->d_iters.p, h->d_status.p, (int)h->batch, h->d_order.p, h->d_code.p);
-    CUDA_TRY(cudaGetLastError());
-    h->order_valid = true;
-    h->launches += 2; // the ADMM kernel and the queue-order kernel
+    // (the queue order of a warm re-solve of these problems and the exit codes are derived when they are asked for: a kernel
+    //  queued here would delay the batch's results until an SM is free for it)
+    h->order_valid = false;
+    h->iters_fresh = true;
+    h->code_valid = false;
+    h->launches += 1;
     h->pending_flags = 0;
+    return GOMP_OK;
+}
+
+int gomp_batch_set_max_ctas(gomp_batch *h, int32_t max_ctas) {
+    if (!h) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
+    if (max_ctas < 0) return fail(GOMP_ERR_INVALID_ARGUMENT, "max_ctas must be >= 0");
+    h->max_ctas = max_ctas;
     return GOMP_OK;
 }
 
@@ -1326,30 +1344,45 @@ static int copy_out(gomp_batch *h, void *dst, const void *src, size_t bytes) {
     return GOMP_OK;
 }
 
-static int queue_results(gomp_batch *h, double *x, double *y, int32_t *exit_code, int32_t *iters, int32_t *rho_updates) {
+// `host_map`: the exit codes go to a host array and the caller waits for the stream: copy OSQP's status values and map them
+// on the host afterwards (gomp_batch_get) -- no kernel, hence no wait for an SM while other batches' CTAs hold them all
+static int queue_results(gomp_batch *h, double *x, double *y, int32_t *exit_code, int32_t *iters, int32_t *rho_updates, bool host_map) {
     const size_t B = (size_t)h->batch;
     int rc;
-    if (exit_code && !h->d_code.p) return fail(GOMP_ERR_INVALID_ARGUMENT, "no solve has been run on this handle");
+    if (exit_code && h->launches == 0) return fail(GOMP_ERR_INVALID_ARGUMENT, "no solve has been run on this handle");
     if ((rc = copy_out(h, x, h->d_xo.p, B * (size_t)h->sym.n * sizeof(double)))) return rc;
     if ((rc = copy_out(h, y, h->d_yo.p, B * (size_t)h->sym.m * sizeof(double)))) return rc;
     if ((rc = copy_out(h, iters, h->d_iters.p, B * sizeof(int)))) return rc;
     if ((rc = copy_out(h, rho_updates, h->d_rup.p, B * sizeof(int)))) return rc;
-    if ((rc = copy_out(h, exit_code, h->d_code.p, B * sizeof(int)))) return rc;
+    if (exit_code && host_map) return copy_out(h, exit_code, h->d_status.p, B * sizeof(int));
+    if (exit_code) {
+        if (!h->code_valid) {
+            if (!h->d_code.p) CUDA_TRY(h->d_code.alloc(B));
+            exit_code_kernel<<<(unsigned)std::min<size_t>((B + 255) / 256, 64), 256, 0, h->stream>>>(h->d_status.p, (int)B, h->d_code.p);
+            CUDA_TRY(cudaGetLastError());
+            h->launches += 1;
+            h->code_valid = true;
+        }
+        if ((rc = copy_out(h, exit_code, h->d_code.p, B * sizeof(int)))) return rc;
+    }
     return GOMP_OK;
 }
 
 int gomp_batch_get_async(gomp_batch *h, double *x, double *y, int32_t *exit_code, int32_t *iters, int32_t *rho_updates) {
     if (!h) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
-    return queue_results(h, x, y, exit_code, iters, rho_updates);
+    return queue_results(h, x, y, exit_code, iters, rho_updates, false);
 }
 
 int gomp_batch_get(gomp_batch *h, double *x, double *y, int32_t *exit_code, int32_t *iters, int32_t *rho_updates) {
     if (!h) return fail(GOMP_ERR_INVALID_ARGUMENT, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
     int rc;
-    if ((rc = queue_results(h, x, y, exit_code, iters, rho_updates))) return rc;
+    const bool host_map = exit_code != nullptr && !is_device_pointer(exit_code);
+    if ((rc = queue_results(h, x, y, exit_code, iters, rho_updates, host_map))) return rc;
     if ((rc = wait_and_check(h))) return rc;
+    if (host_map)
+        for (int64_t b = 0; b < h->batch; ++b) exit_code[b] = exit_code_of(exit_code[b]);
     float ms = 0;
     if (h->launches > 0 && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_solve_ms = ms;
     else cudaGetLastError();

@@ -18,7 +18,7 @@ EXIT_NAMES = ["kOptimal", "kPrimalInfeasible", "kDualInfeasible", "kOptimalInacc
               "kDualInfeasibleInaccurate", "kMaxIterations", "kInterrupted", "kTimeLimitReached", "kNonConvex", "kUnknown"]
 
 EXPORTS = ["gomp_settings_default", "gomp_batch_create", "gomp_batch_setup", "gomp_batch_warm_start_x", "gomp_batch_solve",
-           "gomp_batch_update", "gomp_batch_set_active", "gomp_batch_get", "gomp_batch_get_async", "gomp_batch_get_info", "gomp_batch_get_certificates", "gomp_batch_info", "gomp_batch_sync",
+           "gomp_batch_update", "gomp_batch_set_active", "gomp_batch_set_max_ctas", "gomp_batch_get", "gomp_batch_get_async", "gomp_batch_get_info", "gomp_batch_get_certificates", "gomp_batch_info", "gomp_batch_sync",
            "gomp_batch_destroy", "gomp_batch_device_views", "gomp_device_malloc", "gomp_device_free", "gomp_device_memcpy",
            "gomp_measure_peaks", "gomp_last_error_string", "gomp_device_count", "gomp_version",
            "gomp_mg_create", "gomp_mg_setup", "gomp_mg_warm_start_x", "gomp_mg_update", "gomp_mg_solve", "gomp_mg_get", "gomp_mg_shard",
@@ -175,6 +175,10 @@ class BatchQPSolver:
         p, keep = _ptr(active, dtype=np.int32)
         _check(lib().gomp_batch_set_active(self.h, p))
         self._active_keep = keep
+
+    def set_max_ctas(self, max_ctas):
+        """Cap on the CTAs of the following solves (0 = all): how a caller with several batches in flight shares the SMs."""
+        _check(lib().gomp_batch_set_max_ctas(self.h, C.c_int32(int(max_ctas))))
 
     def solve_async(self):
         _check(lib().gomp_batch_solve(self.h))

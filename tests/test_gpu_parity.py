@@ -429,6 +429,45 @@ def test_active_mask_freezes_problems(env):
     ref.close()
 
 
+def test_max_ctas_and_exit_code_paths(env):
+    """gomp_batch_set_max_ctas: a batch served by fewer CTAs (how several batches in flight share the SMs, bench.py's
+    lanes) gives bit-identical results, cold and in the warm re-solve that orders its queue by the previous iteration
+    counts; the exit codes mapped on the host (gomp_batch_get with a host array) equal the ones mapped on the device
+    (gomp_batch_get_async into a device array); a negative cap is refused."""
+    import torch
+    pkg, O, pat = env
+    B = 640
+    d = pkg.problem.generate(pat, 2100, B)
+    st = pkg.solver.default_settings(prefer_throughput=1)
+    full, capped = make_solver(pkg, pat, d, settings=st), make_solver(pkg, pat, d, settings=st)
+    capped.set_max_ctas(5)
+    outs = []
+    for s in (full, capped):
+        s.set_warm_start(d["x0"])
+        outs.append(s.solve(want_y=True))
+    ref = oracle_batch(O, pat, d)
+    compare(outs[0], ref)
+    for k in ("x", "y", "iters", "exit_code", "rho_updates"):
+        np.testing.assert_array_equal(outs[0][k], outs[1][k])
+    code_dev = torch.empty(B, dtype=torch.int32, device="cuda")
+    capped.get_async(exit_code=code_dev)
+    capped.sync()
+    np.testing.assert_array_equal(code_dev.cpu().numpy(), outs[1]["exit_code"])
+    upd = pkg.problem.relinearize(pat, 2100, np.where(np.isnan(outs[0]["x"]), d["x0"], outs[0]["x"]))
+    capped.set_max_ctas(0)
+    full.set_max_ctas(37)
+    again = []
+    for s in (full, capped):
+        s.update(upd["A_val"], upd["l"], upd["u"])
+        again.append(s.solve(want_y=True))
+    for k in ("x", "y", "iters", "exit_code", "rho_updates"):
+        np.testing.assert_array_equal(again[0][k], again[1][k])
+    with pytest.raises(Exception):
+        full.set_max_ctas(-1)
+    full.close()
+    capped.close()
+
+
 def test_full_batch_kkt_properties():
     """BASELINE configs[1] at its full size (4096 QPs, more than the oracle is asked to solve in a test) through properties that
     do not need the oracle: every QP reported optimal satisfies OSQP's own termination criteria, evaluated here from the
