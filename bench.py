@@ -108,6 +108,7 @@ PIPE = int(os.environ.get("GOMP_BENCH_PIPE", "12"))
 # last ones (fewer than LANES to come) get the wider share -- 20 steps: 268 k without, 281 k with that ramp.  The device-
 # resident leg enqueues every step before the first one has finished; there the ramp only delays the lanes (307 k -> 301 k).
 LANES = int(os.environ.get("GOMP_BENCH_LANES", "4"))
+GATHER = os.environ.get("GOMP_BENCH_GATHER", "1") != "0"  # A/B switch: the per-step NCCL gather of the multi-GPU runs
 
 
 def lane_ctas(k, nsteps, num_sms, ramp):
