@@ -219,7 +219,8 @@ def strong_scaling(pkg, pat, rank, world, local_rank, torch, dist):
     if total <= 0:
         return None
     chunk = int(os.environ.get("GOMP_BENCH_STRONG_CHUNK", "16384"))
-    nh = 4
+    nh = int(os.environ.get("GOMP_BENCH_STRONG_HANDLES", "4"))
+    lanes = int(os.environ.get("GOMP_BENCH_STRONG_LANES", "2"))   # chunks co-resident on the SMs (gomp_batch_set_max_ctas)
     lo, hi = pkg.sharding.shard_range(total, rank, world)   # contiguous id ranges, sizes differ by at most one
     count = hi - lo
     chunk = max(1, min(chunk, count))
@@ -237,6 +238,8 @@ def strong_scaling(pkg, pat, rank, world, local_rank, torch, dist):
         st = S.default_settings(borrow_inputs=1, stream=streams[k].cuda_stream, device=local_rank)
         solvers.append(S.BatchQPSolver(pat.n, pat.m, pat.P_colptr, pat.P_rowidx, pat.P_val, pat.A_colptr, pat.A_rowidx, batch=chunk,
                                        settings=st, var_order=pat.var_order, block_size=pat.block_size))
+        if lanes > 1:
+            solvers[-1].set_max_ctas(-(-solvers[-1].info()["num_sms"] // lanes))
         sc = P.DeviceScene(pat, None, chunk, device=local_rank)
         sc.set_template(tmpl)
         scenes.append(sc)
