@@ -515,6 +515,23 @@ __device__ __forceinline__ void duo_ell_lines(const DevDuo &X, uint32_t mine, ui
         _Pragma("unroll") for (int g = 0; g < G; ++g) sts_f64((aVal) + LO16(e[g]), a__[g] * facarr[g0 + g]); \
     })
 
+// value = (value * fac[slot]) * vec[operand] for the slot's entries (OSQP's row scaling, then its column scaling, in that
+// order of rounding); nrm[slot] = max(nrm[slot], |new value|)
+#define DUO_SCALE2_ABSMAX(ROWSEL, N, facarr, nrmarr, aVal, aVec, mine, pad)                          \
+    duo_ell_lines<ROWSEL, N>(X, mine, pad, [&](auto g0c, const auto &e) {                            \
+        constexpr int g0 = decltype(g0c)::value, G = (int)(sizeof(e) / sizeof(e[0]));                \
+        double a__[G], v__[G];                                                                       \
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {                                              \
+            a__[g] = lds_f64((aVal) + LO16(e[g]));                                                   \
+            v__[g] = lds_f64((aVec) + HI16(e[g]));                                                   \
+        }                                                                                            \
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {                                              \
+            const double t__ = (a__[g] * facarr[g0 + g]) * v__[g];                                   \
+            sts_f64((aVal) + LO16(e[g]), t__);                                                       \
+            nrmarr[g0 + g] = fmax(nrmarr[g0 + g], fabs(t__));                                        \
+        }                                                                                            \
+    })
+
 #define ROWS_LOOP(j, i) _Pragma("unroll") for (int j = 0, i = oid; j < RPT; ++j, i += kDuoOwners) if (i < mu)
 #define COLS_LOOP(c, p8) _Pragma("unroll") for (int c = 0; c < CPT; ++c) if (const int p8 = pos8[c]; p8 >= 0)
 // entries e = (8 position << 16 | 8 value index) of the row this thread owns in slot j
@@ -640,9 +657,15 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
         // ------------------------------------------------------------------ Ruiz equilibration
         {
             double cscale = 1.0;
-            double Ei[RPT], Dp[CPT], qv[CPT];
+            double Dp[CPT], qv[CPT];
+            // E accumulates in the (still unused) w region, one entry per owned row; rn: row norms of A for the coming pass --
+            // a pass scales A in ONE row-view traversal ((a * e_row) * d_col, the column factors read from the right-hand-side
+            // region where they are published for P anyway) and takes the next pass's row norms from the values it writes:
+            // two traversals of A per pass (column norms, scale) instead of four
+            double rn[RPT];
+            ROWS_LOOP(j, i) sts_f64(aW + (uint32_t)i * 8u, 1.0);
 #pragma unroll
-            for (int j = 0; j < RPT; ++j) Ei[j] = 1.0;
+            for (int j = 0; j < RPT; ++j) rn[j] = 0.0;
 #pragma unroll
             for (int c = 0; c < CPT; ++c) { qv[c] = 0.0; Dp[c] = 1.0; }
             if (hasq) {
@@ -661,28 +684,25 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                 for (int q = 0; q < PFW; ++q) pfe[c][q] = q < X.plen[c] ? X.pf_ell[X.pbase[c] + q * kDuoOwners + oid] : ppad;
 #pragma unroll
             for (int k = 0; k < PPT; ++k) puij[k] = oid + k * kDuoOwners < S.nnzPu ? S.Pu_ij[oid + k * kDuoOwners] : 0u;
+            if (st.scaling > 0) DUO_ABSMAX(true, RPT, rn, aA, aRowMine, rpad);
 #pragma unroll 1
             for (int it = 0; it < st.scaling; ++it) {
                 double dt[CPT], et[RPT];
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) dt[c] = 0.0;
 #pragma unroll
-                for (int j = 0; j < RPT; ++j) et[j] = 0.0;
-#pragma unroll
                 for (int c = 0; c < CPT; ++c)
 #pragma unroll
                     for (int q = 0; q < PFW; ++q) dt[c] = fmax(dt[c], fabs(lds_f64(aP + LO16(pfe[c][q]))));
                 DUO_ABSMAX(false, CPT, dt, aA, aColMine, cpad);
-                DUO_ABSMAX(true, RPT, et, aA, aRowMine, rpad);
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) dt[c] = 1.0 / sqrt(limit_scaling(dt[c]));
 #pragma unroll
-                for (int j = 0; j < RPT; ++j) et[j] = 1.0 / sqrt(limit_scaling(et[j]));
+                for (int j = 0; j < RPT; ++j) { et[j] = 1.0 / sqrt(limit_scaling(rn[j])); rn[j] = 0.0; }
                 COLS_LOOP(c, p8) sts_f64(aR + (uint32_t)p8, dt[c]);
                 OWNERS_SYNC();
-                DUO_SCALE(true, RPT, et, aA, aRowMine, rpad);
-#pragma unroll
-                for (int j = 0; j < RPT; ++j) Ei[j] *= et[j];
+                DUO_SCALE2_ABSMAX(true, RPT, et, rn, aA, aR, aRowMine, rpad);
+                ROWS_LOOP(j, i) sts_f64(aW + (uint32_t)i * 8u, lds_f64(aW + (uint32_t)i * 8u) * et[j]);
 #pragma unroll
                 for (int k = 0; k < PPT; ++k) {
                     const int kk = oid + k * kDuoOwners;
@@ -692,7 +712,6 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                 }
                 OWNERS_SYNC();
                 double psum = 0.0, qn[1] = {0.0};
-                DUO_SCALE(false, CPT, dt, aA, aColMine, cpad);
                 COLS_LOOP(c, p8) {
                     qv[c] *= dt[c];
                     Dp[c] *= dt[c];
@@ -712,6 +731,10 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                 cscale *= ct;
                 OWNERS_SYNC();
             }
+            double Ei[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) Ei[j] = 1.0;
+            ROWS_LOOP(j, i) Ei[j] = lds_f64(aW + (uint32_t)i * 8u);
             const size_t bmu = (size_t)b * mu, bnp = (size_t)b * np;
             ROWS_LOOP(j, i) {
                 sts_f64(aLo + (uint32_t)i * 8u, lds_f64(aLo + (uint32_t)i * 8u) * Ei[j]);
