@@ -558,6 +558,10 @@ __device__ __forceinline__ void duo_ell_lines(const DevDuo &X, uint32_t mine, ui
         }                                                                                  \
     } while (0)
 
+// st.shared without the compiler-level memory clobber of sts_f64: global loads of later rows may be scheduled ahead of it
+// (shared-memory accesses are all volatile asm and keep their order among themselves)
+static __device__ __forceinline__ void sts_f64_nc(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+
 template <int RPT, int CPT, int NB>
 static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const DevBatch &B, const DevSettings &st, const DevDuo &X, int slot, int oid) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -629,18 +633,48 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
             const double *gA = B.A_val + (size_t)b * B.A_pitch;
             for (int k = oid; k < S.nnzA; k += kDuoOwners) sts_f64(aA + (uint32_t)k * 8u, gA[k]);
         }
-        for (int k = oid; k < S.nnzPu; k += kDuoOwners) sts_f64(aP + (uint32_t)k * 8u, S.Pu_val[k]);
+        for (int k0 = oid; k0 < S.nnzPu; k0 += 4 * kDuoOwners) { // (four loads in flight per step: the stores are compiler barriers)
+            double v_[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) v_[g] = k0 + g * kDuoOwners < S.nnzPu ? S.Pu_val[k0 + g * kDuoOwners] : 0.0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                if (k0 + g * kDuoOwners < S.nnzPu) sts_f64(aP + (uint32_t)(k0 + g * kDuoOwners) * 8u, v_[g]);
+        }
         {
             const double *gl = B.l + (size_t)b * S.m, *gu = B.u + (size_t)b * S.m;
-            ROWS_LOOP(j, i) {
-                const int orig = S.used_rows[i];
-                sts_f64(aLo + (uint32_t)i * 8u, fmax(gl[orig], -kInfty)); // osqp-cpp clips bounds to +-OSQP_INFTY
-                sts_f64(aHi + (uint32_t)i * 8u, fmin(gu[orig], kInfty));
+            {   // (all of a thread's bounds requested before the first shared-memory store: the stores are compiler barriers,
+                //  and row by row every row cost a dependent L2 + DRAM round trip of its own)
+                int orig_[RPT];
+                double lo_[RPT], hi_[RPT];
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) orig_[j] = oid + j * kDuoOwners < mu ? S.used_rows[oid + j * kDuoOwners] : -1;
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    lo_[j] = orig_[j] >= 0 ? gl[orig_[j]] : 0.0;
+                    hi_[j] = orig_[j] >= 0 ? gu[orig_[j]] : 0.0;
+                }
+                ROWS_LOOP(j, i) {
+                    sts_f64(aLo + (uint32_t)i * 8u, fmax(lo_[j], -kInfty)); // osqp-cpp clips bounds to +-OSQP_INFTY
+                    sts_f64(aHi + (uint32_t)i * 8u, fmin(hi_[j], kInfty));
+                }
             }
             double bad[1] = {0.0};
-            for (int e = oid; e < S.n_empty; e += kDuoOwners) {
-                const int r = S.empty_rows[e];
-                if (!(gl[r] <= 0.0 && 0.0 <= gu[r])) bad[0] = 1.0;
+            // (eight rows per step: the index loads, then the sixteen bound loads of a step are in flight together -- the bounds
+            //  come from DRAM, one dependent round trip per row made this loop two thirds of the load phase)
+            for (int e0 = oid; e0 < S.n_empty; e0 += 8 * kDuoOwners) {
+                int r_[8];
+                double lo_[8], hi_[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) r_[g] = e0 + g * kDuoOwners < S.n_empty ? S.empty_rows[e0 + g * kDuoOwners] : -1;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    lo_[g] = r_[g] >= 0 ? gl[r_[g]] : 0.0;
+                    hi_[g] = r_[g] >= 0 ? gu[r_[g]] : 0.0;
+                }
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    if (!(lo_[g] <= 0.0 && 0.0 <= hi_[g])) bad[0] = 1.0;
             }
             if (B.bulk_ok) {
                 unsigned spins = 0;
@@ -796,10 +830,20 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                 sts_f64(aTab + 48u, 1.0 / kRhoMin);
             }
             if (flags & 2) { // osqp_warm_start_x: x <- Dinv x0, z <- A x
-                COLS_LOOP(c, p8) {
-                    const int var = S.pos_var[p8 >> 3];
-                    x[c] = var >= 0 ? (1.0 / B.Dg[bnp + (p8 >> 3)]) * B.x0[(size_t)b * S.n + var] : 0.0;
-                    sts_f64(aR + (uint32_t)p8, x[c]);
+                {   // (loads first, shared-memory stores after: see the bounds above)
+                    int var_[CPT];
+                    double d_[CPT], x0_[CPT];
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) var_[c] = pos8[c] >= 0 ? S.pos_var[pos8[c] >> 3] : -1;
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) {
+                        d_[c] = pos8[c] >= 0 ? B.Dg[bnp + (pos8[c] >> 3)] : 1.0;
+                        x0_[c] = var_[c] >= 0 ? B.x0[(size_t)b * S.n + var_[c]] : 0.0;
+                    }
+                    COLS_LOOP(c, p8) {
+                        x[c] = var_[c] >= 0 ? (1.0 / d_[c]) * x0_[c] : 0.0;
+                        sts_f64(aR + (uint32_t)p8, x[c]);
+                    }
                 }
                 OWNERS_SYNC();
 #pragma unroll
@@ -1078,7 +1122,7 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                             } else if (l_ < -kInfty * kMinScaling) {
                                 d = fmax(d, 0.0);
                             }
-                            sts_f64(aW + (uint32_t)i * 8u, d);
+                            sts_f64_nc(aW + (uint32_t)i * 8u, d); // (delta_y and E of the other rows are requested ahead of it)
                             nrm[0] = fmax(nrm[0], fabs(uns ? B.Eg[bmu + i] * d : d));
                             lhs += u_ * fmax(d, 0.0) + l_ * fmin(d, 0.0);
                         }
@@ -1174,7 +1218,14 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                 B.z_state[bmu + i] = infeasible ? 0.0 : z[j];
                 B.y_state[bmu + i] = infeasible ? 0.0 : y[j];
             }
-            for (int e = oid; e < S.n_empty; e += kDuoOwners) yo[S.empty_rows[e]] = infeasible ? qnan : 0.0;
+            for (int e0 = oid; e0 < S.n_empty; e0 += 8 * kDuoOwners) {
+                int r_[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) r_[g] = e0 + g * kDuoOwners < S.n_empty ? S.empty_rows[e0 + g * kDuoOwners] : -1;
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    if (r_[g] >= 0) yo[r_[g]] = infeasible ? qnan : 0.0;
+            }
             if (oid == 0) {
                 B.rho_state[b] = lds_f64(aTab);
                 B.status[b] = status;
