@@ -756,7 +756,7 @@ static __device__ __forceinline__ void duo_owner_role(const DevSym &S, const Dev
                     qn[0] = fmax(qn[0], fabs(qv[c]));
                 }
                 psum = duo_sum(psum, sRed, oid, bOwn);
-                duo_max<1>(qn, sRed, oid, bOwn);
+                if (hasq) duo_max<1>(qn, sRed, oid, bOwn); // (q = 0: the norm is 0 on every thread without asking the others)
                 double ct = fmax(psum / (double)S.n, limit_scaling(qn[0]));
                 ct = 1.0 / limit_scaling(ct);
                 for (int k = oid; k < S.nnzPu; k += kDuoOwners) sts_f64(aP + (uint32_t)k * 8u, lds_f64(aP + (uint32_t)k * 8u) * ct);
