@@ -169,7 +169,8 @@ int gomp_batch_update(gomp_batch *h, const double *A_val, const double *l, const
                       const double *q);
 
 /* Results of the last solve.  Any pointer may be NULL.  x: [batch, n], y: [batch, m],
- * exit_code/iters/rho_updates: [batch] int32.  x, y are NaN for infeasible problems. */
+ * exit_code/iters/rho_updates: [batch] int32.  x, y are NaN for infeasible problems.  Waits for the handle's stream;
+ * with a host exit_code array OSQP's status values are copied and mapped to OsqpExitCode on the host (no kernel). */
 int gomp_batch_get(gomp_batch *h, double *x, double *y, int32_t *exit_code, int32_t *iters,
                    int32_t *rho_updates);
 
@@ -204,10 +205,11 @@ int gomp_batch_set_active(gomp_batch *h, const int32_t *active);
  * the knob a caller who keeps SEVERAL batches in flight on one GPU uses to share the SMs between them.  A batch's CTAs are
  * persistent -- they leave their SM only when the batch's work queue is empty -- so with the default, batches run one
  * after the other and each ends with its longest solves (a max_iter QP: ~45 ms on 4096 x (N=7, H=50)) alone on their SMs.
- * With a cap of num_sms / L, L batches are co-resident, a batch lasts L times longer than its longest solve matters, and
- * the stragglers of one batch overlap with the bulk of the others: 4096 x (N=7, H=50), 12 handles, L = 4 (37 CTAs):
- * 315 k -> 337 k QP/s steady state.  A caller that knows its queue is running empty lifts the cap for the last batches
- * (bench.py: L = min(4, batches already in flight + 1, batches still to come + 1)). */
+ * With a cap of num_sms / L, L batches are co-resident, a batch lasts L times longer (about as long as its longest solve),
+ * and the stragglers of one batch overlap with the bulk of the others: 4096 x (N=7, H=50), 12 handles, L = 4 (37 CTAs):
+ * 315 k -> 337 k QP/s steady state.  Needs more handles in flight than L.  A caller that feeds host buffers and knows its
+ * own queue widens the share of the first and last batches (bench.py, lane_ctas: L = min(4, batches already in flight + 1,
+ * batches still to come + 1) in the host-buffer leg; a constant L where every step is queued up front). */
 int gomp_batch_set_max_ctas(gomp_batch *h, int32_t max_ctas);
 
 /* Device-side views of a handle, for callers that keep an SQP round on the GPU without linking the CUDA runtime
