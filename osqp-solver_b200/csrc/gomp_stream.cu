@@ -160,6 +160,27 @@ __device__ __forceinline__ void row_scale_ell2(const DevStream &X, int mu, int i
         (void)q1; (void)q2;
     })
 }
+// A[k] = (A[k] * row factor) * column factor of the entry's position -- OSQP's row scaling, then its column scaling, in that
+// order of rounding -- and the rows' new max norms, in one traversal (the cluster Ruiz kernel: the column factors of the pass
+// are complete before any row is scaled)
+__device__ __forceinline__ void row_scale2_absmax_ell2(const DevStream &X, int mu, int i1, int i2, bool two, double *A, double s1, double s2,
+                                                       const double *dcol, double &r1, double &r2) {
+    double a1 = 0.0, a2 = 0.0;
+    ELL_ROW2(i1, i2, {
+        const double v1 = A[k1], v2 = A[k2], d1 = dcol[q1], d2 = dcol[q2];
+        const double t1 = (v1 * s1) * d1, t2 = (v2 * s2) * d2;
+        if (h1) {
+            A[k1] = t1;
+            a1 = fmax(a1, fabs(t1));
+        }
+        if (h2 && two) {
+            A[k2] = t2;
+            a2 = fmax(a2, fabs(t2));
+        }
+    })
+    r1 = a1;
+    r2 = a2;
+}
 // columns: values are the contiguous CSC range of the column, their compact rows come from the ELL view
 #define ELL_COL2(p1, p2, ...)                                                               \
     const uint32_t rg1 = __ldg(S.col_range + (p1)), rg2 = __ldg(S.col_range + (p2));       \
@@ -1576,10 +1597,24 @@ __global__ void __launch_bounds__(kStreamThreads, 1) gomp_ruiz_cluster_kernel(co
         }
         csync();
         double cscale = 1.0;
+        // Row norms of A for the first pass (et holds, per row, the max norm of the row as it stands; every row belongs to the
+        // same thread in every phase).  From then on a pass traverses A twice instead of four times: the column norms, and ONE
+        // row-view traversal that scales an entry by its row factor and then by its column factor and takes the next pass's row
+        // norm from what it writes.
+        if (st.scaling > 0) {
+            for (int i = gt; i < mu; i += 2 * GT) {
+                const bool two = i + GT < mu;
+                const int i2 = two ? i + GT : i;
+                double na, nb_;
+                row_absmax_ell2(X, mu, i, i2, A, na, nb_);
+                et[i] = na;
+                if (two) et[i2] = nb_;
+            }
+        }
 #pragma unroll 1
         for (int it = 0; it < st.scaling; ++it) {
-            // ---- norms of the KKT columns: variables (P and A columns), constraints (A rows); two at a time on the ELL views,
-            // as the in-kernel phase does (these loops are L2-latency bound: independent loads first)
+            // ---- norms of the KKT columns (P and A columns); two at a time on the ELL views, as the in-kernel phase does
+            // (these loops are L2-latency bound: independent loads first)
             for (int p = gt; p < np; p += 2 * GT) {
                 const bool two = p + GT < np;
                 const int p2 = two ? p + GT : p;
@@ -1589,23 +1624,20 @@ __global__ void __launch_bounds__(kStreamThreads, 1) gomp_ruiz_cluster_kernel(co
                 dt[p] = 1.0 / sqrt(limit_scaling(fmax(pa, na)));
                 if (two) dt[p2] = 1.0 / sqrt(limit_scaling(fmax(pb, nb_)));
             }
-            for (int i = gt; i < mu; i += 2 * GT) {
-                const bool two = i + GT < mu;
-                const int i2 = two ? i + GT : i;
-                double na, nb_;
-                row_absmax_ell2(X, mu, i, i2, A, na, nb_);
-                et[i] = 1.0 / sqrt(limit_scaling(na));
-                if (two) et[i2] = 1.0 / sqrt(limit_scaling(nb_));
-            }
             csync();
-            // ---- rows of A and E by the row factors, P by the column factors on both sides
+            // ---- A by the row factors, then by the column factors; E; P by the column factors on both sides
             for (int i = gt; i < mu; i += 2 * GT) {
                 const bool two = i + GT < mu;
                 const int i2 = two ? i + GT : i;
-                const double ea = et[i], eb = et[i2];
-                row_scale_ell2(X, mu, i, i2, two, A, ea, eb);
+                const double ea = 1.0 / sqrt(limit_scaling(et[i])), eb = 1.0 / sqrt(limit_scaling(et[i2]));
+                double na, nb_;
+                row_scale2_absmax_ell2(X, mu, i, i2, two, A, ea, eb, dt, na, nb_);
+                et[i] = na;
                 E[i] *= ea;
-                if (two) E[i2] *= eb;
+                if (two) {
+                    et[i2] = nb_;
+                    E[i2] *= eb;
+                }
             }
 #pragma unroll 4
             for (int k = gt; k < S.nnzPu; k += GT) {
@@ -1613,13 +1645,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) gomp_ruiz_cluster_kernel(co
                 P[k] = (P[k] * dt[ij >> 16]) * dt[ij & 0xFFFFu];
             }
             csync();
-            // ---- columns of A, D and q by the column factors; cost normalisation from the scaled P
+            // ---- D and q by the column factors; cost normalisation from the scaled P
             double psum = 0.0, qn = 0.0;
             for (int p = gt; p < np; p += 2 * GT) {
                 const bool two = p + GT < np;
                 const int p2 = two ? p + GT : p;
                 const double da = dt[p], db = dt[p2];
-                col_scale2(S, X, p, p2, two, A, da, db);
                 D[p] *= da;
                 if (two) D[p2] *= db;
                 if (hasq) {
