@@ -680,6 +680,28 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             row_scale_ell2(X, mu, i1, i2, two, gA, s1, s2);
         }
     };
+    // A = (A * row factor) * column factor of the entry's position, and the rows' new max norms (see row_scale2_absmax_ell2)
+    auto row_scale2_absmax = [&](int i1, int i2, bool two, double s1, double s2, const double *dcol, double &r1, double &r2) {
+        if (SM) {
+            double a[2] = {0.0, 0.0};
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                if (w == 1 && !two) break;
+                const uint32_t rg = row_range(w ? i2 : i1);
+                const double sc = w ? s2 : s1;
+                for (int q = (int)(rg >> 8), q1 = q + (int)(rg & 0xFFu); q < q1; ++q) {
+                    const uint32_t e = sRowEnt[q];
+                    const double t = (gA[e & 0xFFFFu] * sc) * dcol[e >> 16];
+                    gA[e & 0xFFFFu] = t;
+                    a[w] = fmax(a[w], fabs(t));
+                }
+            }
+            r1 = a[0];
+            r2 = a[1];
+        } else {
+            row_scale2_absmax_ell2(X, mu, i1, i2, two, gA, s1, s2, dcol, r1, r2);
+        }
+    };
     auto col_dot2 = [&](int p1, int p2, const double *vec, double &r1, double &r2) {
         if (SM) {
             r1 = col_dot4(col_range(p1), gA, sCscRow, vec, r1);
@@ -805,6 +827,17 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             for (int q = pfptr[p_], q1 = pfptr[p_ + 1]; q < q1; ++q) nrm = fmax(nrm, fabs(Pv[pfent[q] & 0xFFFFu]));
             return nrm;
         };
+        // gW holds, per row, the max norm of the row as it stands (every row belongs to the same thread in every phase): a pass
+        // traverses A twice -- the column norms, and one row-view traversal that scales an entry by its row factor, then by its
+        // column factor, and takes the next pass's row norm from what it writes -- instead of four times
+        if (st.scaling > 0) {
+            ROWS2(i, i2, two) {
+                double na, nb;
+                row_absmax2(i, i2, na, nb);
+                gW[i] = na;
+                if (two) gW[i2] = nb;
+            }
+        }
 #pragma unroll 1
         for (int it = 0; it < st.scaling; ++it) {
             COLS2(p, p2, two) {
@@ -814,18 +847,17 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
                 dtv[p] = 1.0 / sqrt(limit_scaling(fmax(pa, na)));
                 if (two) dtv[p2] = 1.0 / sqrt(limit_scaling(fmax(pb, nb)));
             }
-            ROWS2(i, i2, two) {
-                double na, nb;
-                row_absmax2(i, i2, na, nb);
-                gW[i] = 1.0 / sqrt(limit_scaling(na));
-                if (two) gW[i2] = 1.0 / sqrt(limit_scaling(nb));
-            }
             __syncthreads();
             ROWS2(i, i2, two) {
-                const double ea = gW[i], eb = gW[i2];
-                row_scale2(i, i2, two, ea, eb);
+                const double ea = 1.0 / sqrt(limit_scaling(gW[i])), eb = 1.0 / sqrt(limit_scaling(gW[i2]));
+                double na, nb;
+                row_scale2_absmax(i, i2, two, ea, eb, dtv, na, nb);
+                gW[i] = na;
                 Ev[i] *= ea;
-                if (two) Ev[i2] *= eb;
+                if (two) {
+                    gW[i2] = nb;
+                    Ev[i2] *= eb;
+                }
             }
 #pragma unroll 4
             for (int k = tid; k < S.nnzPu; k += kST) {
@@ -836,7 +868,6 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) gomp_admm_stream_kernel
             double psum = 0.0, qn[1] = {0.0};
             COLS2(p, p2, two) {
                 const double da = dtv[p], db = dtv[p2];
-                col_scale_2(p, p2, two, da, db);
                 gD[p] *= da;
                 if (two) gD[p2] *= db;
                 if (hasq) {
