@@ -1034,6 +1034,20 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_con
                 qv[c] = (hasq && var >= 0) ? B.q[(size_t)b * S.n + var] : 0.0;
                 Dp[c] = 1.0;
             }
+            // rn: max norms of the owned rows as they stand.  A pass traverses A twice -- the column norms, and one row-view
+            // traversal that scales an entry by its row factor, then by its column factor (OSQP's order of rounding; the column
+            // factors of the pass are published in sRHS for P anyway) and takes the next pass's row norm from what it writes --
+            // instead of four times
+            double rn[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) rn[j] = 0.0;
+            if (st.scaling > 0) {
+                ROWS_LOOP(j, i) {
+                    double nrm = 0.0;
+                    ROW_ENTRIES(i, e) nrm = fmax(nrm, fabs(sA[e & 0xFFFFu]));
+                    rn[j] = nrm;
+                }
+            }
 #pragma unroll 1
             for (int it = 0; it < st.scaling; ++it) {
                 double dt[CPT], et[RPT];
@@ -1044,14 +1058,16 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_con
                     dt[c] = 1.0 / sqrt(limit_scaling(nrm));
                     sRHS[p] = dt[c];
                 }
-                ROWS_LOOP(j, i) {
-                    double nrm = 0.0;
-                    ROW_ENTRIES(i, e) nrm = fmax(nrm, fabs(sA[e & 0xFFFFu]));
-                    et[j] = 1.0 / sqrt(limit_scaling(nrm));
-                }
+                ROWS_LOOP(j, i) et[j] = 1.0 / sqrt(limit_scaling(rn[j]));
                 owners_sync();
                 ROWS_LOOP(j, i) {
-                    ROW_ENTRIES(i, e) sA[e & 0xFFFFu] *= et[j];
+                    double nrm = 0.0;
+                    ROW_ENTRIES(i, e) {
+                        const double t = (sA[e & 0xFFFFu] * et[j]) * sRHS[e >> 16];
+                        sA[e & 0xFFFFu] = t;
+                        nrm = fmax(nrm, fabs(t));
+                    }
+                    rn[j] = nrm;
                     Ei[j] *= et[j];
                 }
                 for (int k = oid; k < S.nnzPu; k += kOwners) {
@@ -1061,7 +1077,6 @@ __global__ void __launch_bounds__(kThreads, 1) gomp_admm_kernel(const __grid_con
                 owners_sync();
                 double psum = 0.0, qn[1] = {0.0};
                 COLS_LOOP(c, p) {
-                    COL_ENTRIES(p, k) sA[k] *= dt[c];
                     qv[c] *= dt[c];
                     Dp[c] *= dt[c];
                     double nrm = 0.0;
