@@ -86,7 +86,12 @@ struct QP {
         D.assign(np, 1.0);
         E.assign(mu, 1.0);
         c = 1.0;
-        std::vector<double> dt(np), et(mu);
+        // As the device kernels do it: rn holds the rows' max norms as they stand; a pass takes the column norms, then scales
+        // every entry in one row-view traversal -- (a * e_row) * d_col, OSQP's row scaling followed by its column scaling --
+        // and takes the next pass's row norms from the values it writes (two traversals of A per pass instead of four).
+        std::vector<double> dt(np), et(mu), rn(mu, 0.0);
+        if (st.scaling > 0)
+            for (int i = 0; i < mu; ++i) forRow(i, [&](int, int k) { rn[i] = std::max(rn[i], std::fabs(sA[k])); });
         for (int it = 0; it < st.scaling; ++it) {
             for (int p = 0; p < np; ++p) {
                 double nrm = 0;
@@ -95,12 +100,14 @@ struct QP {
                 dt[p] = 1.0 / std::sqrt(limit(nrm));
             }
             for (int i = 0; i < mu; ++i) {
+                et[i] = 1.0 / std::sqrt(limit(rn[i]));
                 double nrm = 0;
-                forRow(i, [&](int, int k) { nrm = std::max(nrm, std::fabs(sA[k])); });
-                et[i] = 1.0 / std::sqrt(limit(nrm));
+                forRow(i, [&](int pos, int k) {
+                    sA[k] = (sA[k] * et[i]) * dt[pos];
+                    nrm = std::max(nrm, std::fabs(sA[k]));
+                });
+                rn[i] = nrm;
             }
-            for (int i = 0; i < mu; ++i) forRow(i, [&](int, int k) { sA[k] *= et[i]; });
-            for (int p = 0; p < np; ++p) forCol(p, [&](int, int k) { sA[k] *= dt[p]; });
             for (size_t k = 0; k < sP.size(); ++k) {
                 uint32_t ij = S->Pu_ij[k];
                 sP[k] = (sP[k] * dt[ij >> 16]) * dt[ij & 0xFFFF];
